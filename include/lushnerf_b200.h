@@ -1,0 +1,177 @@
+/*
+ * lushnerf_b200.h -- C ABI of the B200-native LuSh-NeRF per-ray volumetric rendering hot path.
+ *
+ * The reference (quzefan/LuSh-NeRF) is pure PyTorch with no FFI of its own, so this header IS the
+ * boundary a maintainer binds (ctypes stub in INTEGRATION.md).  Every entry point cites the reference
+ * function it replaces as  file:line  relative to the reference root.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless stated
+ *   - all tensors are contiguous row-major fp32 unless stated; nullable pointers are marked
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream)
+ *   - return value: 0 on success, negative LUSH_E* on argument errors, positive cudaError_t on a
+ *     CUDA failure; never throws.  lush_last_error() gives a human-readable message (thread-local).
+ *   - kernels never allocate: scratch comes in through `workspace` (size from the *_workspace_bytes
+ *     query of the same op)
+ */
+#ifndef LUSHNERF_B200_H_
+#define LUSHNERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LUSH_ABI_VERSION 1
+
+#define LUSH_OK 0
+#define LUSH_EINVAL (-1)      /* bad argument / unsupported shape */
+#define LUSH_EWORKSPACE (-2)  /* workspace too small */
+#define LUSH_EUNSUPPORTED (-3)
+
+int lush_abi_version(void);
+const char* lush_last_error(void);
+/* Number of kernels launched by this library since process start (bench.py: "gpu_launches"). */
+int64_t lush_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ray preparation.  Replaces the prologue shared by render_infer / render_train_scene /
+ * render_train_noise (models/lushnerf.py:706-729, 772-795, 827-850) and ndc_rays
+ * (utils/run_lushnerf_helpers.py:542-562):
+ *   viewdirs = d/|d| (before NDC);  NDC warp with near plane 1 and focal K[0][0];
+ *   ray_batch = [o(3) d(3) near far viewdirs(3)]  ->  [R,11]
+ * rays is [R,3,2] (last axis: origin, direction).  ndc=0 skips the warp.
+ * ------------------------------------------------------------------------------------------- */
+int lush_ray_prep_fwd(const float* rays, float* ray_batch, int64_t R, int H, int W, double focal,
+                      float near, float far, int ndc, void* stream);
+/* g_ray_batch [R,11] -> g_rays [R,3,2] (written, not accumulated). */
+int lush_ray_prep_bwd(const float* rays, const float* g_ray_batch, float* g_rays, int64_t R, int H,
+                      int W, double focal, int ndc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Coarse sample placement.  Replaces models/lushnerf.py:389-412 (render_rays) / :501-523:
+ *   t = linspace(0,1,S) (passed in as t_vals[S], computed by the host exactly as the reference
+ *   does), z = near(1-t)+far t (or the lindisp form), optional stratified jitter with t_rand[R,S]
+ *   (nullable: no perturbation).  z_out [R,S].
+ * ------------------------------------------------------------------------------------------- */
+int lush_stratified_z(const float* ray_batch, int ray_stride, const float* t_vals,
+                      const float* t_rand, float* z_out, int64_t R, int S, int lindisp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Alpha compositing.  Replaces NeRFAll.raw2outputs (models/lushnerf.py:296-352).
+ *   raw [R,S,4], z [R,S], rays_d: R rows of 3 floats with row stride `d_stride` floats,
+ *   sigma_noise [R,S-1] nullable (already multiplied by raw_noise_std),
+ *   rm_near_thresh: density_i *= (z_{i+1} > thresh) when >= 0 (eval branch, :331-335; pass -1 in
+ *   training), white_bkgd: rgb += 1-acc (:349-350).
+ *   outputs: rgb_map [R,3], density [R,S-1], acc [R], weights [R,S], depth [R]
+ *   (density / weights nullable when the caller does not need them).
+ *   flags (nullable int32[1]): bit0 |= any NaN, bit1 |= any Inf in the outputs (replaces the
+ *   isnan/isinf host syncs at :474-478).
+ * ------------------------------------------------------------------------------------------- */
+int lush_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride,
+                       const float* sigma_noise, float rm_near_thresh, int white_bkgd,
+                       float* rgb_map, float* density, float* acc, float* weights, float* depth,
+                       int* flags, int64_t R, int S, void* stream);
+/* Backward of the above (closed form).  Upstream grads (all nullable = zero):
+ *   g_rgb [R,3], g_density [R,S-1], g_acc [R], g_weights [R,S], g_depth [R].
+ * Outputs: g_raw [R,S,4] (written), g_rays_d [R,3] nullable (written; dense stride 3). */
+int lush_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride,
+                       const float* sigma_noise, float rm_near_thresh, int white_bkgd,
+                       const float* g_rgb, const float* g_density, const float* g_acc,
+                       const float* g_weights, const float* g_depth, float* g_raw, float* g_rays_d,
+                       int64_t R, int S, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Hierarchical sampling.  Replaces sample_pdf (utils/run_lushnerf_helpers.py:566-609).
+ *   bins [R,nb], weights [R,nb-1]  (nb = S-1 at the render_rays call site, :435-436)
+ *   u: det -> u is [N] shared by all rays (u_stride = 0); random -> [R,N] (u_stride = N)
+ *   cdf_in (nullable) [R,nb]: STRICT mode, the caller supplies the reference-computed cdf and the
+ *     kernel only searches/gathers/lerps.  When null the cdf is built in-kernel with the association
+ *     order documented in DESIGN.md (bit-exact against oracle.sample_pdf(order="kernel")).
+ *   samples [R,N];  inds_out (nullable) int64 [R,N] = searchsorted(cdf, u, right=True).
+ * ------------------------------------------------------------------------------------------- */
+int lush_sample_pdf(const float* bins, const float* weights, const float* cdf_in, const float* u,
+                    int64_t u_stride, float* samples, int64_t* inds_out, int64_t R, int nb, int N,
+                    void* stream);
+/* Fused fine-sample placement: z_mid + sample_pdf(weights[:,1:-1]) + sort(cat(z, z_samples))
+ * (models/lushnerf.py:435-440 / :544-549) + z_std (:465).  z [R,S], weights [R,S] (full weights of the
+ * coarse pass).  Outputs z_fine [R,S+N] sorted ascending, z_samples [R,N], z_std [R] nullable. */
+int lush_sample_merge(const float* z, const float* weights, const float* u, int64_t u_stride,
+                      float* z_fine, float* z_samples, float* z_std, int64_t R, int S, int N,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Encoder + MLP.  Replaces Embedder.forward (helpers:311-344), NeRF.forward (helpers:394-423),
+ * NeRF_Noise.forward (helpers:483-512), NeRFAll.mlpforward / mlpforward_noise
+ * (models/lushnerf.py:234-293).
+ *
+ * lush_mlp_desc describes the network; `params` is ONE flat fp32 buffer holding the tensors in
+ * state_dict order:  pts_linears.{0..D-1}.{weight,bias}, views_linears.0.{weight,bias},
+ * feature_linear.{weight,bias}, alpha_linear.{weight,bias}, rgb_linear.{weight,bias}
+ * (each weight [out,in] row-major, as nn.Linear stores it).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lush_mlp_desc {
+  int32_t D;           /* number of pts_linears */
+  int32_t W;           /* hidden width */
+  int32_t L_pts;       /* multires (10) -> input_ch = 3 + 6*L_pts */
+  int32_t L_views;     /* multires_views (4) -> input_ch_views = 3 + 6*L_views */
+  int32_t skip;        /* skip layer index (4); -1 = none */
+  int32_t out_mode;    /* 0: scene MLP, out = [rgb(3), sigma(1)];  1: noise MLP, out = rgb(3) */
+} lush_mlp_desc;
+
+/* Number of fp32 elements in the flat parameter buffer for `desc`. */
+int64_t lush_mlp_param_count(const lush_mlp_desc* desc);
+
+/* Sample-point generation is fused in: for ray r and sample s the network input is
+ *   x = o_r + d_r * z[r,s]   (models/lushnerf.py:414 / :441), viewdir v_r shared by the ray.
+ * ray_batch [R, ray_stride] with o at col 0, d at col 3, viewdirs at col 8.  z [R,S].
+ * For the noise MLP (out_mode 1) the reference evaluates ONE point per ray, sample index 16 of the
+ * un-jittered coarse z (models/lushnerf.py:271): pass S=1 and z = that column.
+ * out: [R*S, 4] (mode 0) or [R*S, 3] (mode 1).
+ * impl: 0 = fp32 SIMT (exact-fp32 parity mode), 1 = fp16-operand/fp32-accumulate tcgen05 path.
+ * `stash` (nullable) receives the activations needed by lush_mlp_bwd (size from
+ * lush_mlp_stash_bytes); pass null for inference. */
+size_t lush_mlp_workspace_bytes(const lush_mlp_desc* desc, int64_t R, int S, int impl, int training);
+size_t lush_mlp_stash_bytes(const lush_mlp_desc* desc, int64_t R, int S, int impl);
+int lush_mlp_fwd(const lush_mlp_desc* desc, const float* params, const float* ray_batch,
+                 int ray_stride, const float* z, float* out, void* stash, void* workspace,
+                 size_t workspace_bytes, int64_t R, int S, int impl, void* stream);
+/* Backward.  g_out like out.  g_params: flat fp32 buffer like params, ACCUMULATED into (caller
+ * zeroes).  g_ray_batch (nullable) [R,11]: written with d/d(o), d/d(d), 0, 0, d/d(viewdirs). */
+int lush_mlp_bwd(const lush_mlp_desc* desc, const float* params, const float* ray_batch,
+                 int ray_stride, const float* z, const float* g_out, const void* stash,
+                 float* g_params, float* g_ray_batch, void* workspace, size_t workspace_bytes,
+                 int64_t R, int S, int impl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rigid-warp blur kernel.  Replaces Rigid_Blurring_Kernel.rbk_warp (models/lushnerf.py:75-98) and
+ * SE3Field.warp / Rigid_body.exp_se3 (utils/rigid_warping.py:20-140).
+ *   rays [N,3,2]; r, v [N,3,M] (already multiplied by rv_window, as at :144-145);
+ *   new_rays [N, M+1, 3, 2] with slot 0 = the original ray (use_origin, :83-84).
+ * ------------------------------------------------------------------------------------------- */
+int lush_rbk_warp_fwd(const float* rays, const float* r, const float* v, float* new_rays, int64_t N,
+                      int M, void* stream);
+int lush_rbk_warp_bwd(const float* rays, const float* r, const float* v, const float* g_new_rays,
+                      float* g_rays, float* g_r, float* g_v, int64_t N, int M, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K-ray blend + noise add + tone map.  Replaces rbk_weighted_sum (models/lushnerf.py:100-116) for
+ * rgb, the 0.1*sigmoid(noise) add (:649) and ToneMapping('gamma') (helpers:164-174):
+ *   blended[n] = sum_k ccw[n,k] * rgb[n*K+k];  noise_rgb = 0.1*sigmoid(noise_raw) (nullable)
+ *   out_blur = tm(blended + noise_rgb), out_pure = tm(blended);  tm(x) = x^(1/2.2) if gamma else x
+ * K=1 with ccw null degenerates to tone mapping only.
+ * ------------------------------------------------------------------------------------------- */
+int lush_blend_tonemap_fwd(const float* rgb, const float* ccw, const float* noise_raw,
+                           float* out_blur, float* out_pure, float* noise_rgb, int64_t N, int K,
+                           int gamma, void* stream);
+int lush_blend_tonemap_bwd(const float* rgb, const float* ccw, const float* noise_raw,
+                           const float* g_blur, const float* g_pure, const float* g_noise_rgb,
+                           float* g_rgb, float* g_ccw, float* g_noise_raw, int64_t N, int K,
+                           int gamma, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUSHNERF_B200_H_ */

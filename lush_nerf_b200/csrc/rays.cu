@@ -1,0 +1,418 @@
+// Per-ray elementwise kernels: ray preparation (normalise + NDC), coarse sample placement,
+// rigid-warp blur kernel (SE(3) exp map) forward/backward, K-ray blend + tone map forward/backward.
+// All are tiny, HBM/latency-bound; one thread per ray (or pixel).  Compiled with --fmad=false so the
+// fp32 results follow the reference's unfused op sequence.
+#include "common.cuh"
+
+namespace lush {
+
+struct NdcConst {
+  float cx, cy;  // -1/(W/(2f)), -1/(H/(2f))  (reference helpers:551-556, Python double -> fp32)
+};
+
+// ------------------------------------------------------------------------------------------------
+// ray_prep  (reference models/lushnerf.py:706-729 + helpers:542-562)
+// ------------------------------------------------------------------------------------------------
+__global__ void ray_prep_fwd_kernel(const float* __restrict__ rays, float* __restrict__ out,
+                                    int64_t R, NdcConst k, float near, float far, int ndc) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float* p = rays + r * 6;
+  float ox = p[0], dx = p[1], oy = p[2], dy = p[3], oz = p[4], dz = p[5];
+  float n = sqrtf(dx * dx + dy * dy + dz * dz);
+  float vx = dx / n, vy = dy / n, vz = dz / n;
+  float o0 = ox, o1 = oy, o2 = oz, d0 = dx, d1 = dy, d2 = dz;
+  if (ndc) {
+    float t = -(1.f + oz) / dz;
+    float px = ox + t * dx, py = oy + t * dy, pz = oz + t * dz;
+    o0 = k.cx * px / pz;
+    o1 = k.cy * py / pz;
+    o2 = 1.f + 2.f / pz;
+    d0 = k.cx * (dx / dz - px / pz);
+    d1 = k.cy * (dy / dz - py / pz);
+    d2 = -2.f / pz;
+  }
+  float* q = out + r * 11;
+  q[0] = o0; q[1] = o1; q[2] = o2; q[3] = d0; q[4] = d1; q[5] = d2;
+  q[6] = near; q[7] = far; q[8] = vx; q[9] = vy; q[10] = vz;
+}
+
+__global__ void ray_prep_bwd_kernel(const float* __restrict__ rays, const float* __restrict__ g,
+                                    float* __restrict__ g_rays, int64_t R, NdcConst k, int ndc) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float* p = rays + r * 6;
+  float ox = p[0], dx = p[1], oy = p[2], dy = p[3], oz = p[4], dz = p[5];
+  const float* gq = g + r * 11;
+  float go0 = gq[0], go1 = gq[1], go2 = gq[2], gd0 = gq[3], gd1 = gq[4], gd2 = gq[5];
+  float gv0 = gq[8], gv1 = gq[9], gv2 = gq[10];
+  float gox, goy, goz, gdx, gdy, gdz;
+  if (ndc) {
+    float t = -(1.f + oz) / dz;
+    float px = ox + t * dx, py = oy + t * dy, pz = oz + t * dz;
+    float a = px / pz, b = py / pz;
+    float ga = k.cx * (go0 - gd0), gb = k.cy * (go1 - gd1);
+    float gpx = ga / pz, gpy = gb / pz;
+    float gpz = (-ga * a - gb * b) / pz + 2.f * (gd2 - go2) / (pz * pz);
+    gdx = k.cx * gd0 / dz;
+    gdy = k.cy * gd1 / dz;
+    gdz = -(k.cx * gd0 * dx + k.cy * gd1 * dy) / (dz * dz);
+    // p = o + t d
+    float gt = gpx * dx + gpy * dy + gpz * dz;
+    gox = gpx; goy = gpy; goz = gpz;
+    gdx += t * gpx; gdy += t * gpy; gdz += t * gpz;
+    // t = -(1+oz)/dz
+    goz += -gt / dz;
+    gdz += gt * (1.f + oz) / (dz * dz);
+  } else {
+    gox = go0; goy = go1; goz = go2; gdx = gd0; gdy = gd1; gdz = gd2;
+  }
+  // viewdirs = d/|d|
+  float n = sqrtf(dx * dx + dy * dy + dz * dz);
+  float vx = dx / n, vy = dy / n, vz = dz / n;
+  float dot = vx * gv0 + vy * gv1 + vz * gv2;
+  gdx += (gv0 - vx * dot) / n;
+  gdy += (gv1 - vy * dot) / n;
+  gdz += (gv2 - vz * dot) / n;
+  float* q = g_rays + r * 6;
+  q[0] = gox; q[1] = gdx; q[2] = goy; q[3] = gdy; q[4] = goz; q[5] = gdz;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stratified z  (reference models/lushnerf.py:389-412)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float z_at(float near, float far, float t, int lindisp) {
+  if (!lindisp) return near * (1.f - t) + far * t;
+  return 1.f / (1.f / near * (1.f - t) + 1.f / far * t);
+}
+
+__global__ void stratified_z_kernel(const float* __restrict__ ray_batch, int ray_stride,
+                                    const float* __restrict__ t_vals,
+                                    const float* __restrict__ t_rand, float* __restrict__ z_out,
+                                    int64_t R, int S, int lindisp) {
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= R * S) return;
+  int64_t r = idx / S;
+  int s = (int)(idx - r * S);
+  float near = ray_batch[r * ray_stride + 6], far = ray_batch[r * ray_stride + 7];
+  float zc = z_at(near, far, t_vals[s], lindisp);
+  if (t_rand != nullptr) {
+    float lower = zc, upper = zc;
+    if (s > 0) lower = 0.5f * (zc + z_at(near, far, t_vals[s - 1], lindisp));
+    if (s < S - 1) upper = 0.5f * (z_at(near, far, t_vals[s + 1], lindisp) + zc);
+    zc = lower + (upper - lower) * t_rand[idx];
+  }
+  z_out[idx] = zc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rigid-warp blur kernel (reference models/lushnerf.py:75-98, utils/rigid_warping.py:20-140)
+// ------------------------------------------------------------------------------------------------
+struct V3 {
+  float x, y, z;
+};
+__device__ __forceinline__ V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+  return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+
+struct Se3 {
+  V3 w, u;           // unit axis, scaled translation
+  float th, s, c1, k;  // theta, sin, 1-cos, theta-sin
+  V3 au, bu, p;
+};
+
+__device__ __forceinline__ Se3 se3_make(V3 rot, V3 trans) {
+  Se3 e;
+  float nr = sqrtf(dot(rot, rot));
+  e.th = nr + 1.0e-10f;
+  e.w = mk(rot.x / e.th, rot.y / e.th, rot.z / e.th);
+  e.u = mk(trans.x / e.th, trans.y / e.th, trans.z / e.th);
+  float sn, cs;
+  sincosf(e.th, &sn, &cs);
+  e.s = sn;
+  e.c1 = 1.f - cs;
+  e.k = e.th - sn;
+  e.au = cross(e.w, e.u);
+  e.bu = cross(e.w, e.au);
+  e.p = e.th * e.u + e.c1 * e.au + e.k * e.bu;
+  return e;
+}
+__device__ __forceinline__ V3 se3_apply(const Se3& e, V3 x) {
+  V3 a = cross(e.w, x);
+  V3 b = cross(e.w, a);
+  return x + e.s * a + e.c1 * b + e.p;
+}
+
+__global__ void rbk_warp_fwd_kernel(const float* __restrict__ rays, const float* __restrict__ r,
+                                    const float* __restrict__ v, float* __restrict__ out, int64_t N,
+                                    int M) {
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= N * (M + 1)) return;
+  int64_t n = idx / (M + 1);
+  int m = (int)(idx - n * (M + 1));
+  const float* p = rays + n * 6;
+  V3 o = mk(p[0], p[2], p[4]), d = mk(p[1], p[3], p[5]);
+  float* q = out + idx * 6;
+  if (m == 0) {
+    q[0] = o.x; q[1] = d.x; q[2] = o.y; q[3] = d.y; q[4] = o.z; q[5] = d.z;
+    return;
+  }
+  int mm = m - 1;
+  const float* rp = r + n * 3 * M;
+  const float* vp = v + n * 3 * M;
+  Se3 e = se3_make(mk(rp[mm], rp[M + mm], rp[2 * M + mm]), mk(vp[mm], vp[M + mm], vp[2 * M + mm]));
+  V3 yo = se3_apply(e, o);
+  V3 ye = se3_apply(e, o + d);
+  V3 yd = ye - yo;
+  q[0] = yo.x; q[1] = yd.x; q[2] = yo.y; q[3] = yd.y; q[4] = yo.z; q[5] = yd.z;
+}
+
+// reverse of y = x + s (w x x) + c1 (w x (w x x)) for upstream g; accumulates gw, gs, gc1, returns gx
+__device__ __forceinline__ V3 rot_apply_bwd(const Se3& e, V3 x, V3 g, V3& gw, float& gs, float& gc1) {
+  V3 a = cross(e.w, x);
+  V3 b = cross(e.w, a);
+  gs += dot(g, a);
+  gc1 += dot(g, b);
+  V3 ga = e.s * g;
+  V3 gb = e.c1 * g;
+  // b = w x a
+  gw = gw + cross(a, gb);
+  ga = ga + cross(gb, e.w);
+  // a = w x x
+  gw = gw + cross(x, ga);
+  return g + cross(ga, e.w);
+}
+
+__global__ void rbk_warp_bwd_kernel(const float* __restrict__ rays, const float* __restrict__ r,
+                                    const float* __restrict__ v, const float* __restrict__ g_out,
+                                    float* __restrict__ g_rays, float* __restrict__ g_r,
+                                    float* __restrict__ g_v, int64_t N, int M) {
+  int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* p = rays + n * 6;
+  V3 o = mk(p[0], p[2], p[4]), d = mk(p[1], p[3], p[5]);
+  const float* g0 = g_out + n * (M + 1) * 6;
+  V3 go = mk(g0[0], g0[2], g0[4]), gd = mk(g0[1], g0[3], g0[5]);
+  const float* rp = r + n * 3 * M;
+  const float* vp = v + n * 3 * M;
+  for (int mm = 0; mm < M; ++mm) {
+    const float* gq = g0 + (mm + 1) * 6;
+    V3 gyo = mk(gq[0], gq[2], gq[4]), gyd = mk(gq[1], gq[3], gq[5]);
+    V3 rot = mk(rp[mm], rp[M + mm], rp[2 * M + mm]);
+    V3 trans = mk(vp[mm], vp[M + mm], vp[2 * M + mm]);
+    Se3 e = se3_make(rot, trans);
+    V3 gye = gyd;
+    V3 gyo_t = gyo - gyd;
+    V3 gp = gyo;  // = gye + gyo_t
+    V3 gw = mk(0, 0, 0);
+    float gs = 0.f, gc1 = 0.f;
+    V3 gx_o = rot_apply_bwd(e, o, gyo_t, gw, gs, gc1);
+    V3 gx_e = rot_apply_bwd(e, o + d, gye, gw, gs, gc1);
+    go = go + gx_o + gx_e;
+    gd = gd + gx_e;
+    // p = th*u + c1*au + k*bu
+    float gth = dot(gp, e.u);
+    V3 gu = e.th * gp;
+    gc1 += dot(gp, e.au);
+    float gk = dot(gp, e.bu);
+    V3 gau = e.c1 * gp;
+    V3 gbu = e.k * gp;
+    gw = gw + cross(e.au, gbu);
+    gau = gau + cross(gbu, e.w);
+    gw = gw + cross(e.u, gau);
+    gu = gu + cross(gau, e.w);
+    // k = th - s ; s = sin th ; c1 = 1 - cos th
+    gth += gk;
+    gs -= gk;
+    float cs = 1.f - e.c1;
+    gth += gs * cs + gc1 * e.s;
+    // w = rot/th ; u = trans/th
+    V3 grot = (1.f / e.th) * gw;
+    V3 gtr = (1.f / e.th) * gu;
+    gth += -(dot(gw, e.w) + dot(gu, e.u)) / e.th;
+    // th = |rot| + eps
+    float nr = sqrtf(dot(rot, rot));
+    if (nr > 0.f) grot = grot + (gth / nr) * rot;
+    float* grp = g_r + n * 3 * M;
+    float* gvp = g_v + n * 3 * M;
+    grp[mm] = grot.x; grp[M + mm] = grot.y; grp[2 * M + mm] = grot.z;
+    gvp[mm] = gtr.x;  gvp[M + mm] = gtr.y;  gvp[2 * M + mm] = gtr.z;
+  }
+  float* q = g_rays + n * 6;
+  q[0] = go.x; q[1] = gd.x; q[2] = go.y; q[3] = gd.y; q[4] = go.z; q[5] = gd.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-ray blend + noise + tone map (reference models/lushnerf.py:100-116, 649-654; helpers:164-174)
+// ------------------------------------------------------------------------------------------------
+constexpr float kInvGamma = (float)(1.0 / 2.2);
+
+__global__ void blend_tonemap_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ ccw,
+                                         const float* __restrict__ noise_raw,
+                                         float* __restrict__ out_blur, float* __restrict__ out_pure,
+                                         float* __restrict__ noise_rgb, int64_t N, int K, int gamma) {
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= N * 3) return;
+  int64_t n = idx / 3;
+  int c = (int)(idx - n * 3);
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float wk = ccw ? ccw[n * K + k] : 1.f;
+    acc += rgb[(n * K + k) * 3 + c] * wk;
+  }
+  float nz = 0.f;
+  if (noise_raw) {
+    nz = 0.1f * sigmoidf_(noise_raw[idx]);
+    if (noise_rgb) noise_rgb[idx] = nz;
+  }
+  float xb = acc + nz;
+  if (out_blur) out_blur[idx] = gamma ? powf(xb, kInvGamma) : xb;
+  if (out_pure) out_pure[idx] = gamma ? powf(acc, kInvGamma) : acc;
+}
+
+__global__ void blend_tonemap_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ ccw,
+                                         const float* __restrict__ noise_raw,
+                                         const float* __restrict__ g_blur,
+                                         const float* __restrict__ g_pure,
+                                         const float* __restrict__ g_noise_rgb,
+                                         float* __restrict__ g_rgb, float* __restrict__ g_ccw,
+                                         float* __restrict__ g_noise_raw, int64_t N, int K, int gamma) {
+  int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float gacc[3];
+  for (int c = 0; c < 3; ++c) {
+    int64_t idx = n * 3 + c;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc += rgb[(n * K + k) * 3 + c] * (ccw ? ccw[n * K + k] : 1.f);
+    float sg = 0.f, nz = 0.f;
+    if (noise_raw) {
+      sg = sigmoidf_(noise_raw[idx]);
+      nz = 0.1f * sg;
+    }
+    float gb = g_blur ? g_blur[idx] : 0.f;
+    float gp = g_pure ? g_pure[idx] : 0.f;
+    float gxb = gb, gxp = gp;
+    if (gamma) {
+      gxb = gb * kInvGamma * powf(acc + nz, kInvGamma - 1.f);
+      gxp = gp * kInvGamma * powf(acc, kInvGamma - 1.f);
+      if (gb == 0.f) gxb = 0.f;
+      if (gp == 0.f) gxp = 0.f;
+    }
+    gacc[c] = gxb + gxp;
+    if (g_noise_raw) {
+      float gn = gxb + (g_noise_rgb ? g_noise_rgb[idx] : 0.f);
+      g_noise_raw[idx] = noise_raw ? gn * 0.1f * sg * (1.f - sg) : 0.f;
+    }
+  }
+  for (int k = 0; k < K; ++k) {
+    float wk = ccw ? ccw[n * K + k] : 1.f;
+    float gw = 0.f;
+    for (int c = 0; c < 3; ++c) {
+      int64_t j = (n * K + k) * 3 + c;
+      if (g_rgb) g_rgb[j] = gacc[c] * wk;
+      gw += gacc[c] * rgb[j];
+    }
+    if (g_ccw) g_ccw[n * K + k] = gw;
+  }
+}
+
+}  // namespace lush
+
+using namespace lush;
+
+static NdcConst make_ndc(int H, int W, double focal) {
+  NdcConst k;
+  k.cx = (float)(-1.0 / (W / (2.0 * focal)));
+  k.cy = (float)(-1.0 / (H / (2.0 * focal)));
+  return k;
+}
+
+extern "C" int lush_ray_prep_fwd(const float* rays, float* ray_batch, int64_t R, int H, int W,
+                                 double focal, float near, float far, int ndc, void* stream) {
+  LUSH_REQUIRE(rays && ray_batch && R >= 0, "ray_prep_fwd: null pointer or negative R");
+  if (R == 0) return 0;
+  int th = 256;
+  ray_prep_fwd_kernel<<<(unsigned)ceil_div(R, th), th, 0, (cudaStream_t)stream>>>(
+      rays, ray_batch, R, make_ndc(H, W, focal), near, far, ndc);
+  LUSH_LAUNCH_CHECK("ray_prep_fwd");
+  return 0;
+}
+
+extern "C" int lush_ray_prep_bwd(const float* rays, const float* g_ray_batch, float* g_rays,
+                                 int64_t R, int H, int W, double focal, int ndc, void* stream) {
+  LUSH_REQUIRE(rays && g_ray_batch && g_rays && R >= 0, "ray_prep_bwd: null pointer");
+  if (R == 0) return 0;
+  int th = 256;
+  ray_prep_bwd_kernel<<<(unsigned)ceil_div(R, th), th, 0, (cudaStream_t)stream>>>(
+      rays, g_ray_batch, g_rays, R, make_ndc(H, W, focal), ndc);
+  LUSH_LAUNCH_CHECK("ray_prep_bwd");
+  return 0;
+}
+
+extern "C" int lush_stratified_z(const float* ray_batch, int ray_stride, const float* t_vals,
+                                 const float* t_rand, float* z_out, int64_t R, int S, int lindisp,
+                                 void* stream) {
+  LUSH_REQUIRE(ray_batch && t_vals && z_out && R >= 0 && S >= 1 && ray_stride >= 8,
+               "stratified_z: bad arguments");
+  if (R == 0) return 0;
+  int th = 256;
+  stratified_z_kernel<<<(unsigned)ceil_div(R * S, th), th, 0, (cudaStream_t)stream>>>(
+      ray_batch, ray_stride, t_vals, t_rand, z_out, R, S, lindisp);
+  LUSH_LAUNCH_CHECK("stratified_z");
+  return 0;
+}
+
+extern "C" int lush_rbk_warp_fwd(const float* rays, const float* r, const float* v, float* new_rays,
+                                 int64_t N, int M, void* stream) {
+  LUSH_REQUIRE(rays && r && v && new_rays && N >= 0 && M >= 0, "rbk_warp_fwd: bad arguments");
+  if (N == 0) return 0;
+  int th = 128;
+  rbk_warp_fwd_kernel<<<(unsigned)ceil_div(N * (M + 1), th), th, 0, (cudaStream_t)stream>>>(
+      rays, r, v, new_rays, N, M);
+  LUSH_LAUNCH_CHECK("rbk_warp_fwd");
+  return 0;
+}
+
+extern "C" int lush_rbk_warp_bwd(const float* rays, const float* r, const float* v,
+                                 const float* g_new_rays, float* g_rays, float* g_r, float* g_v,
+                                 int64_t N, int M, void* stream) {
+  LUSH_REQUIRE(rays && r && v && g_new_rays && g_rays && g_r && g_v && N >= 0 && M >= 0,
+               "rbk_warp_bwd: bad arguments");
+  if (N == 0) return 0;
+  int th = 128;
+  rbk_warp_bwd_kernel<<<(unsigned)ceil_div(N, th), th, 0, (cudaStream_t)stream>>>(
+      rays, r, v, g_new_rays, g_rays, g_r, g_v, N, M);
+  LUSH_LAUNCH_CHECK("rbk_warp_bwd");
+  return 0;
+}
+
+extern "C" int lush_blend_tonemap_fwd(const float* rgb, const float* ccw, const float* noise_raw,
+                                      float* out_blur, float* out_pure, float* noise_rgb, int64_t N,
+                                      int K, int gamma, void* stream) {
+  LUSH_REQUIRE(rgb && N >= 0 && K >= 1, "blend_tonemap_fwd: bad arguments");
+  LUSH_REQUIRE(K == 1 || ccw, "blend_tonemap_fwd: ccw required when K > 1");
+  if (N == 0) return 0;
+  int th = 256;
+  blend_tonemap_fwd_kernel<<<(unsigned)ceil_div(N * 3, th), th, 0, (cudaStream_t)stream>>>(
+      rgb, ccw, noise_raw, out_blur, out_pure, noise_rgb, N, K, gamma);
+  LUSH_LAUNCH_CHECK("blend_tonemap_fwd");
+  return 0;
+}
+
+extern "C" int lush_blend_tonemap_bwd(const float* rgb, const float* ccw, const float* noise_raw,
+                                      const float* g_blur, const float* g_pure,
+                                      const float* g_noise_rgb, float* g_rgb, float* g_ccw,
+                                      float* g_noise_raw, int64_t N, int K, int gamma, void* stream) {
+  LUSH_REQUIRE(rgb && N >= 0 && K >= 1, "blend_tonemap_bwd: bad arguments");
+  if (N == 0) return 0;
+  int th = 128;
+  blend_tonemap_bwd_kernel<<<(unsigned)ceil_div(N, th), th, 0, (cudaStream_t)stream>>>(
+      rgb, ccw, noise_raw, g_blur, g_pure, g_noise_rgb, g_rgb, g_ccw, g_noise_raw, N, K, gamma);
+  LUSH_LAUNCH_CHECK("blend_tonemap_bwd");
+  return 0;
+}

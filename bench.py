@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- train rays/s of the LuSh-NeRF per-ray rendering hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode train|render]
+
+One "step" = one pass of the hot path over one batch of synthetic LLFF-shaped rays at the
+poster_lushnerf training configuration (BASELINE.json configs[1]): NeRFAll.forward in rigid-blur-kernel
+mode (N_rand=1024 pixels x K=5 warped rays = 5120 rays, 64 coarse + 64 fine samples, perturb=1,
+raw_noise_std=1) + loss + backward + gradient all-reduce + Adam.  For N>1 every rank renders its own
+N_rand pixels (weak scaling) and the only collective is one flat 5.2 MB gradient all-reduce.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with the batch already resident in HBM;
+`e2e` = the same step driven from pinned host buffers (H2D of the batch + D2H of the loss inside the timed
+region); `roofline` = algorithmic MLP FLOPs / measured MLP device time against the measured bf16 peak;
+`cpu_baseline` = the CPU oracle port on this box's host cores on a bounded sample.
+`--impl reference` times the reference algorithm's CPU implementation (oracle port; the reference tree
+itself cannot travel to the GPU box) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work: scene MLP 593 408 MAC/sample, fwd+bwd = 3x forward
+FLOP_FWD_PER_SAMPLE = 2 * 593408
+N_RAND, K_RAYS, N_SAMPLES, N_IMPORTANCE = 1024, 5, 64, 64
+SAMPLES_PER_RAY = N_SAMPLES + (N_SAMPLES + N_IMPORTANCE)
+H, W, FOCAL = 400, 600, 500.0
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "tflops": d.get("bf16_tflops_sustained", 1400.0),
+                "source": "MEASURED_PEAKS.json (bf16 sustained: kernel timed inside a long step)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1])); mx.append(float(f[2]))
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, n_pixels=32):
+    """fwd+bwd of the poster training step on the CPU oracle; returns (rays/s, ms/step, cores, sample)."""
+    from oracle import lush_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nets = O.det_nets(O.POSTER_CFG, tag=1, sigma_gain=30.0)
+    rbk = O.det_rbk_params(tag=7)
+    pn = {k: {n: t.clone().requires_grad_(True) for n, t in d.items()} for k, d in nets.items()}
+    pr = {n: t.clone().requires_grad_(True) for n, t in rbk.items()}
+    from lush_nerf_b200.synthetic import SyntheticLLFF
+    data = SyntheticLLFF(H, W, FOCAL, max_views=1)
+    R = n_pixels * K_RAYS
+    times = []
+    for it in range(warmup + steps):
+        b = data.batch(it, n_pixels)
+        t0 = time.perf_counter()
+        out, _ = O.nerfall_train_forward(
+            pn, pr, O.POSTER_CFG, b["rays"].contiguous(), b["images_idx"], H, W, FOCAL, N_samples=N_SAMPLES,
+            N_importance=N_IMPORTANCE, allkernel=True, kernel_pixel=b["fq_mask"], t_rand=torch.rand(R, N_SAMPLES),
+            noise_c=torch.randn(R, N_SAMPLES - 1), noise_f=torch.randn(R, N_SAMPLES + N_IMPORTANCE - 1),
+            u=torch.rand(R, N_IMPORTANCE))
+        tgt = b["rgbsf"]
+        loss = 0.5 * ((out[0] - tgt) ** 2).mean() + 0.5 * (out[0] - tgt).abs().mean() \
+            + 0.5 * ((out[1] - tgt) ** 2).mean() + 0.5 * (out[1] - tgt).abs().mean()
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    sample = (f"{n_pixels} pixels x {K_RAYS} rays = {R} rays/step, {N_SAMPLES}+{N_IMPORTANCE} samples, "
+              f"NeRFAll.forward RBK mode fwd+bwd, {steps} timed steps, torch CPU fp32")
+    return R * len(times) / total, 1e3 * total / len(times), cores, sample
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    val, ms, cores, sample = cpu_reference_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "train rays/s (coarse+fine fwd+bwd, 64+64 samples)", "value": val,
+            "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(1),
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "poster_lushnerf training step (BASELINE configs[1]): NeRFAll.forward RBK mode, "
+                        "N_rand=1024 px x K=5 rays = 5120 rays/GPU, N_samples=64, N_importance=64, perturb=1, "
+                        "raw_noise_std=1, scene+noise MLPs, loss, backward, Adam",
+            "rays_per_step_per_gpu": N_RAND * K_RAYS, "image": f"{H}x{W} f={FOCAL}", "views": 20,
+            "parallelism": f"rays sharded x{n_gpus}, one flat grad all-reduce/step" if n_gpus > 1 else "single GPU",
+            "l2": "per-step working set (GBs of activation stash) exceeds the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mlp", default=None, choices=[None, "simt", "tc"], help="override LUSH_MLP_IMPL")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if args.mlp:
+        os.environ["LUSH_MLP_IMPL"] = args.mlp
+    args.warmup = max(args.warmup, 3)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ.setdefault("LUSH_VERBOSE", "0")
+
+    from lush_nerf_b200 import _lib, ops
+    from lush_nerf_b200.synthetic import SyntheticLLFF, build_model, poster_args
+    from lush_nerf_b200.train import Trainer
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    pargs = poster_args()
+    model = build_model(pargs).to(dev)
+    if world > 1:  # identical replicas: broadcast rank 0's initial parameters once
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    render_kwargs = dict(perturb=1.0, N_importance=N_IMPORTANCE, N_samples=N_SAMPLES, use_viewdirs=True,
+                         white_bkgd=False, raw_noise_std=1.0, inference=False, near=0.0, far=1.0)
+    trainer = Trainer(model, H, W, np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]]), lrate=5e-4,
+                      render_kwargs=render_kwargs)
+    data = SyntheticLLFF(H, W, FOCAL, seed=rank, max_views=2)
+    n_batches = args.warmup + args.steps
+    host = [{k: v.contiguous().pin_memory() for k, v in data.batch(i, N_RAND).items()} for i in range(n_batches)]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- MLP timing hook (roofline): CUDA events around every lush_mlp_fwd / lush_mlp_bwd call
+    mlp_events = []
+    ops.MLP_EVENT_SINK = None
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        trainer.step(resident[i])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ops.MLP_EVENT_SINK = mlp_events
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        trainer.step(resident[args.warmup + i])
+    e1.record()
+    barrier()
+    ops.MLP_EVENT_SINK = None
+    launches = _lib.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    mlp_ms = sum(a.elapsed_time(b) for a, b in mlp_events)
+    mlp_calls = len(mlp_events)
+
+    # ---- timed region 2: end to end from pinned host buffers, loss read back every step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        b = {k: v.to(dev, non_blocking=True) for k, v in host[args.warmup + i].items()}
+        loss = trainer.step(b)
+        loss_host = float(loss.item())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = t.tolist()
+    rays_total = N_RAND * K_RAYS * world * args.steps
+    value = rays_total / (ms_total * 1e-3)
+    e2e_val = rays_total / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        flops_step = 3 * FLOP_FWD_PER_SAMPLE * N_RAND * K_RAYS * SAMPLES_PER_RAY
+        achieved = (flops_step * args.steps / (mlp_ms * 1e-3)) / 1e12 if mlp_ms > 0 else None
+        impl_name = {0: "fp32 SIMT (FFMA)", 1: "tcgen05 fp16 operands / fp32 accumulate"}[model.mlp_coarse.impl()]
+        line = {
+            "metric": "train rays/s (coarse+fine fwd+bwd, 64+64 samples)", "value": value, "unit": "rays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32" if model.mlp_coarse.impl() == 0 else "fp16 operands, fp32 accumulate",
+            "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "pixels_per_s": value / K_RAYS,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": None,
+                         "kernel": f"encoder+MLP fwd+bwd ({impl_name}), all launches of the step; algorithmic "
+                                   f"{flops_step / 1e12:.3f} TFLOP/step (3 x 1 186 816 FLOP x 983 040 samples)",
+                         "mlp_ms_per_step": mlp_ms / args.steps, "mlp_calls_per_step": mlp_calls / args.steps,
+                         "peak_source": peaks["source"]},
+            "final_loss": loss_host,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            val, ms, cores, sample = cpu_reference_run(steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,14 @@ int64_t lush_mlp_param_count(const lush_mlp_desc* desc) {
   return L.total;
 }
 
+int lush_mlp_impl_supported(const lush_mlp_desc* desc, int impl) {
+  MlpLayout L;
+  if (!layout_ok(desc, L, "mlp_impl_supported")) return 0;
+  if (impl == 0) return 1;
+  if (impl == 1) return lush_mlp_tc_supported(L) ? 1 : 0;
+  return 0;
+}
+
 size_t lush_mlp_workspace_bytes(const lush_mlp_desc* desc, int64_t R, int S, int impl, int training) {
   MlpLayout L;
   if (!layout_ok(desc, L, "mlp_workspace_bytes") || R < 0 || S < 1) return 0;

@@ -1,0 +1,467 @@
+"""B200-native NeRFAll / RBK with the reference's call surface (models/lushnerf.py of
+quzefan/LuSh-NeRF): same constructor arguments, method names, return structures and state_dict keys, so
+run_lushnerf.py's training and --render_only paths can import this module instead.
+
+What runs where
+  * per-ray work (ray prep + NDC, sample placement, fused encoder+MLP fwd/bwd, alpha compositing
+    fwd/bwd, hierarchical sampling + z merge, SE(3) ray warp fwd/bwd, K-ray blend + tone map) =
+    hand-written sm_100a kernels behind include/lushnerf_b200.h (lush_nerf_b200/ops.py)
+  * the 25 k-parameter view-embedding MLP of the blur kernel (N_rand rows x 64 features) and the
+    random draws (same calls / order as the reference so a shared seed gives the same streams) =
+    PyTorch
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import math
+import os
+import random
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..utils import rigid_warping
+from ..utils.run_lushnerf_helpers import (NeRF, NeRF_Noise, ToneMapping, get_embedder, get_rays)
+
+_GUARD_KEYS = (("rgb_map", 0), ("depth_map", 2), ("acc_map", 4), ("density_map", 6), ("raw", 8))
+
+
+class View_Embedding(nn.Module):
+    """Per-image embedding table (reference :27-35)."""
+
+    def __init__(self, num_embed, embed_dim):
+        super().__init__()
+        self.num_embed, self.embed_dim = num_embed, embed_dim
+        self.view_embed_layer = nn.Embedding(num_embed, embed_dim)
+
+    def forward(self, x):
+        return self.view_embed_layer(x)
+
+
+class Rigid_Blurring_Kernel(nn.Module):
+    """DP-NeRF rigid blurring kernel (reference :37-153): view embedding -> trunk -> (r, v, w) heads ->
+    num_motion SE(3)-warped copies of every ray + composition weights."""
+
+    def __init__(self, D, W, D_r, W_r, D_v, W_v, D_w, W_w, output_ch_r, output_ch_v, input_ch, skips, rv_window,
+                 num_motion=2, near=0.0, far=1.0, ndc=False, warp_field=None, view_embedding_layer=None,
+                 use_origin=True):
+        super().__init__()
+        self.input_ch, self.skips = input_ch, skips
+        self.view_embedding_layer = view_embedding_layer
+        self.view_embed_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)] + [nn.Linear(W, W) if i not in skips else nn.Linear(W + input_ch, W)
+                                        for i in range(D - 1)])
+        self.use_origin = use_origin
+        self.num_motion = num_motion
+        self.output_ch_r, self.output_ch_v = output_ch_r * num_motion, output_ch_v * num_motion
+        self.output_ch_w = num_motion
+        self.rv_window = rv_window
+
+        def branch(depth, width, out_ch, tiny):
+            stack = nn.ModuleList([nn.Linear(W, width)] + [nn.Linear(width, width) for _ in range(depth - 1)])
+            head = nn.Linear(width, out_ch)
+            if tiny:  # heads start at U(-1e-5, 1e-5): the kernel begins as the identity warp (reference :62-68)
+                nn.init.xavier_uniform_(head.weight, gain=0.00001 / math.sqrt((width + out_ch) / 6))
+            return stack, head
+
+        self.r_branch, self.r_linear = branch(D_r, W_r, self.output_ch_r, True)
+        self.v_branch, self.v_linear = branch(D_v, W_v, self.output_ch_v, True)
+        self.w_branch, self.w_linear = branch(D_w, W_w, self.output_ch_w + 1, False)
+        self.warp_field = warp_field
+
+    def rbk_warp(self, rays, r, v):
+        """rays [N,3,2], r/v [N, 3*num_motion] -> [N, K, 3, 2]; one fused kernel for all motions."""
+        N = rays.shape[0]
+        out = ops.rbk_warp(rays, r.reshape(N, 3, self.num_motion), v.reshape(N, 3, self.num_motion))
+        return out if self.use_origin else out[:, 1:]
+
+    def rbk_weighted_sum(self, rgb, depth, acc, extras, ccw):
+        """Blend the K rays of every pixel with ccw (reference :100-116)."""
+        K = self.num_motion + 1 if self.use_origin else self.num_motion
+
+        def blend(v):
+            if v.dim() == 1:
+                return torch.sum(v.reshape(-1, K) * ccw, dim=1)
+            return torch.sum(v.reshape(-1, K, *v.shape[1:]) * ccw.reshape(ccw.shape + (1,) * (v.dim() - 1)), dim=1)
+
+        rgb = blend(rgb)
+        depth, acc = blend(depth), blend(acc)
+        extras = {k: (blend(v) if torch.is_tensor(v) and 1 <= v.dim() <= 3 else v) for k, v in extras.items()}
+        return rgb, depth, acc, extras
+
+    def motion_params(self, rays_info):
+        h = e = self.view_embedding_layer(rays_info['images_idx'].squeeze(-1))
+        for i, l in enumerate(self.view_embed_linears):
+            h = F.relu(l(h))
+            if i in self.skips:
+                h = torch.cat([e, h], -1)
+        hr, hv, hw = h, h, h
+        for l in self.r_branch:
+            hr = F.relu(l(hr))
+        for l in self.v_branch:
+            hv = F.relu(l(hv))
+        for l in self.w_branch:
+            hw = F.relu(l(hw))
+        r = self.r_linear(hr) * self.rv_window
+        v = self.v_linear(hv) * self.rv_window
+        w = torch.sigmoid(self.w_linear(hw))
+        return r, v, w / (torch.sum(w, dim=-1, keepdims=True) + 1e-10)
+
+    def forward(self, rays, rays_info):
+        r, v, w = self.motion_params(rays_info)
+        return self.rbk_warp(rays, r, v).reshape(-1, 3, 2), w
+
+
+class RBK(nn.Module):
+    """Container the driver builds (reference :156-175; kwargs as at run_lushnerf.py:333-338)."""
+
+    def __init__(self, num_img, view_embed_ch, D_rbk, W_rbk, D_rbk_r, W_rbk_r, D_rbk_v, W_rbk_v, D_rbk_w, W_rbk_w,
+                 output_ch_rbk_r, output_ch_rbk_v, skips_rbk, rbk_use_origin, rbk_se_rv_window, num_motion_rbk,
+                 use_dpnerf=True, use_awp=False, near=0.0, far=1.0, ndc=False):
+        super().__init__()
+        self.use_dpnerf = use_dpnerf
+        self.view_embed_ch = view_embed_ch
+        self.view_embed_layer = View_Embedding(num_embed=num_img, embed_dim=view_embed_ch)
+        self.use_awp = use_awp
+        self.SE3Field = rigid_warping.SE3Field()
+        self.RBK = Rigid_Blurring_Kernel(
+            D=D_rbk, W=W_rbk, num_motion=num_motion_rbk, D_r=D_rbk_r, W_r=W_rbk_r, output_ch_r=output_ch_rbk_r,
+            D_v=D_rbk_v, W_v=W_rbk_v, output_ch_v=output_ch_rbk_v, D_w=D_rbk_w, W_w=W_rbk_w,
+            rv_window=rbk_se_rv_window, view_embedding_layer=self.view_embed_layer, use_origin=rbk_use_origin,
+            input_ch=view_embed_ch, skips=skips_rbk, near=near, far=far, ndc=ndc, warp_field=self.SE3Field)
+
+
+class NeRFAll(nn.Module):
+    def __init__(self, args, blur_kernel_net=None):
+        super().__init__()
+        self.args = args
+        self.blur_model_type = args.blur_model_type
+        self.blur_kernel_net = blur_kernel_net
+        self.embed_fn, self.input_ch = get_embedder(args.multires, args.i_embed)
+        self.input_ch_views, self.embeddirs_fn = 0, None
+        if args.use_viewdirs:
+            self.embeddirs_fn, self.input_ch_views = get_embedder(args.multires_views, args.i_embed)
+        self.output_ch = 5 if args.N_importance > 0 else 4
+        self.use_awp = False
+        skips = [4]
+        common = dict(input_ch=self.input_ch, skips=skips, input_ch_views=self.input_ch_views,
+                      use_viewdirs=args.use_viewdirs, use_awp=False)
+        self.mlp_coarse = NeRF(D=args.netdepth, W=args.netwidth, output_ch=self.output_ch, **common)
+        self.mlp_noise_coarse = NeRF_Noise(D=args.netdepth // 2, W=args.netwidth // 2, output_ch=3, **common)
+        self.mlp_fine = None
+        if args.N_importance > 0:
+            self.mlp_fine = NeRF(D=args.netdepth_fine, W=args.netwidth_fine, output_ch=self.output_ch, **common)
+        if blur_kernel_net is not None and self.blur_model_type == 'dpnerf':
+            self.dbk_view_embedding = blur_kernel_net.view_embed_layer
+            self.mlp_rbk = blur_kernel_net.RBK
+        if args.rgb_activate != 'sigmoid' or getattr(args, 'sigma_activate', 'relu') != 'relu':
+            raise NotImplementedError("the compositing kernel implements rgb_activate='sigmoid', "
+                                      "sigma_activate='relu' (every shipped config)")
+        self.tonemapping = ToneMapping(args.tone_mapping_type)
+        # Optional hook `fn(kind, shape, device) -> tensor` ("rand" / "randn") replacing the torch draws, so
+        # parity tests can feed the exact numbers the reference consumed.
+        self.rng_override = None
+        self._flags = None          # device int32[1]: NaN/Inf bits written by the compositing kernel
+        self._flags_pending = None  # pinned host copy from the previous call (lazy guard)
+
+    # ------------------------------------------------------------------------------------------
+    # numerical guard: replaces ~20 isnan/isinf host syncs per call (reference :474-478) by one flag word
+    # ------------------------------------------------------------------------------------------
+    def _guard_flags(self, device):
+        if self._flags is None or self._flags.device != device:
+            self._flags = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._flags
+
+    def _guard_report(self, device, tag=""):
+        mode = os.environ.get("LUSH_NUMERIC_GUARD", "lazy")
+        if mode == "off" or self._flags is None:
+            return
+        if self._flags_pending is not None and (mode == "sync" or self._flags_pending[1].query()):
+            host, ev = self._flags_pending
+            ev.synchronize()
+            self._print_flags(int(host.item()))
+            self._flags_pending = None
+        if self._flags_pending is None:
+            host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+            host.copy_(self._flags, non_blocking=True)
+            self._flags.zero_()
+            ev = torch.cuda.Event()
+            ev.record()
+            self._flags_pending = (host, ev)
+            if mode == "sync":
+                ev.synchronize()
+                self._print_flags(int(host.item()))
+                self._flags_pending = None
+
+    @staticmethod
+    def _print_flags(bits):
+        for key, sh in _GUARD_KEYS:
+            if bits >> sh & 1:
+                print(f"! [Numerical Error] {key} contains nan.")
+            if bits >> sh & 2:
+                print(f"! [Numerical Error] {key} contains inf.")
+
+    def _draw(self, kind, shape, device):
+        if self.rng_override is not None:
+            return self.rng_override(kind, list(shape), device)
+        return torch.rand(shape, device=device) if kind == "rand" else torch.randn(shape, device=device)
+
+    # ------------------------------------------------------------------------------------------
+    # network application
+    # ------------------------------------------------------------------------------------------
+    def mlpforward(self, inputs, viewdirs, mlp, force_naive=True, inference=False, netchunk=1024 * 64):
+        """inputs [R,S,3] points, viewdirs [R,3] -> [R,S,4]  (reference :234-266).  The fused kernel
+        takes (o, d, z); points given explicitly are fed as o = x, d = 0, one sample per pseudo-ray.
+        netchunk is accepted for compatibility; activations never leave the chip in chunks."""
+        R, S = inputs.shape[0], inputs.shape[1]
+        pts = inputs.reshape(-1, 3)
+        vd = viewdirs[:, None].expand(R, S, 3).reshape(-1, 3) if viewdirs is not None else torch.zeros_like(pts)
+        rb = torch.cat([pts, torch.zeros_like(pts), torch.zeros_like(pts[:, :2]), vd], -1)
+        out = mlp.render(rb, torch.zeros_like(pts[:, :1]))
+        return out.reshape(R, S, -1)
+
+    def mlpforward_noise(self, inputs, viewdirs, mlp, force_naive=True, inference=False, netchunk=1024 * 64):
+        """Noise MLP on sample index 16 of every ray (reference :268-293) -> [R,3]."""
+        pts = inputs[:, 16]
+        rb = torch.cat([pts, torch.zeros_like(pts), torch.zeros_like(pts[:, :2]), viewdirs], -1)
+        return mlp.render(rb, torch.zeros_like(pts[:, :1]))[:, 0, :]
+
+    def raw2outputs(self, raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
+        """(rgb_map, density, acc_map, weights, depth_map)  (reference :296-352)."""
+        noise = None
+        if raw_noise_std > 0.:
+            noise = torch.randn_like(raw[..., :-1, 3]) * raw_noise_std
+            if pytest:
+                np.random.seed(0)
+                noise = torch.tensor(np.random.rand(*list(raw[..., :-1, 3].shape)) * raw_noise_std,
+                                     dtype=raw.dtype, device=raw.device)
+        return ops.composite(raw, z_vals, rays_d, noise, self._rm_near_thresh(), white_bkgd,
+                             self._guard_flags(raw.device))
+
+    def _rm_near_thresh(self):
+        if not self.training and self.args.render_rmnearplane > 0:
+            return self.args.render_rmnearplane / 128
+        return -1.0
+
+    # ------------------------------------------------------------------------------------------
+    # render_rays family (reference :354-617): one implementation, three entry points
+    # ------------------------------------------------------------------------------------------
+    def _noise_branch(self, ray_batch, N_samples, lindisp):
+        rb = ray_batch.detach()
+        t16 = ops.linspace01(N_samples, rb.device)[16:17]   # IndexError-equivalent: N_samples must be >= 17
+        if t16.numel() == 0:
+            raise IndexError("index 16 is out of bounds for dimension 1 with size %d" % N_samples)
+        z16 = ops.stratified_z(rb, t16, None, lindisp)
+        return self.mlp_noise_coarse.render(rb, z16)[:, 0, :]
+
+    def _render(self, ray_batch, N_samples, retraw, lindisp, perturb, N_importance, white_bkgd, raw_noise_std,
+                scene=True, noise=True):
+        dev = ray_batch.device
+        R = ray_batch.shape[0]
+        rays_d = ray_batch[:, 3:6]
+        ret, ret_noise = {}, {}
+        if noise:
+            ret_noise['rgb_map'] = self._noise_branch(ray_batch, N_samples, lindisp)
+        if not scene:
+            return ret, ret_noise
+        flags = self._guard_flags(dev)
+        thresh = self._rm_near_thresh()
+        t_vals = ops.linspace01(N_samples, dev)
+        t_rand = self._draw("rand", [R, N_samples], dev) if perturb > 0. else None
+        z = ops.stratified_z(ray_batch, t_vals, t_rand, lindisp)
+        raw = self.mlp_coarse.render(ray_batch, z)
+        nz = self._draw("randn", [R, N_samples - 1], dev) * raw_noise_std if raw_noise_std > 0. else None
+        rgb_map, density, acc, weights, depth = ops.composite(raw, z, rays_d, nz, thresh, white_bkgd, flags)
+        if N_importance > 0:
+            rgb0, depth0, acc0, density0 = rgb_map, depth, acc, density
+            u = ops.linspace01(N_importance, dev) if perturb == 0. else self._draw("rand", [R, N_importance], dev)
+            z, z_samples, z_std = ops.sample_merge(z, weights, u)
+            mlp = self.mlp_coarse if self.mlp_fine is None else self.mlp_fine
+            raw = mlp.render(ray_batch, z)
+            nz = self._draw("randn", [R, z.shape[1] - 1], dev) * raw_noise_std if raw_noise_std > 0. else None
+            rgb_map, density, acc, weights, depth = ops.composite(raw, z, rays_d, nz, thresh, white_bkgd, flags)
+        ret.update(rgb_map=rgb_map, depth_map=depth, acc_map=acc, density_map=density)
+        if retraw:
+            ret['raw'] = raw
+            if noise:
+                ret_noise['raw'] = 0
+        if N_importance > 0:
+            ret.update(rgb0=rgb0, depth0=depth0, acc0=acc0, density0=density0, z_std=z_std)
+            if noise:
+                ret_noise['rgb0'] = ret_noise['rgb_map']
+        self._guard_report(dev)
+        return ret, ret_noise
+
+    def render_rays(self, ray_batch, N_samples, img_idx=None, retraw=False, lindisp=False, perturb=0.,
+                    N_importance=0, white_bkgd=False, raw_noise_std=0., pytest=False, force_naive=False,
+                    inference=False):
+        """Scene (coarse + fine) and noise branches -> (ret, ret_noise)  (reference :354-479)."""
+        return self._render(ray_batch, N_samples, retraw, lindisp, perturb, N_importance, white_bkgd,
+                            raw_noise_std, scene=True, noise=True)
+
+    def render_rays_nonoise(self, ray_batch, N_samples, img_idx=None, retraw=False, lindisp=False, perturb=0.,
+                            N_importance=0, white_bkgd=False, raw_noise_std=0., pytest=False, force_naive=False,
+                            inference=False):
+        """Scene branch only -> ret  (reference :481-583)."""
+        return self._render(ray_batch, N_samples, retraw, lindisp, perturb, N_importance, white_bkgd,
+                            raw_noise_std, scene=True, noise=False)[0]
+
+    def render_rays_noise(self, ray_batch, N_samples, img_idx=None, retraw=False, lindisp=False, perturb=0.,
+                          N_importance=0, white_bkgd=False, raw_noise_std=0., pytest=False, force_naive=False,
+                          inference=False):
+        """Noise branch only -> ret_noise  (reference :585-617)."""
+        return self._render(ray_batch, N_samples, retraw, lindisp, perturb, N_importance, white_bkgd,
+                            raw_noise_std, scene=False, noise=True)[1]
+
+    # ------------------------------------------------------------------------------------------
+    # ray batches (reference :679-866)
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _focal(K):
+        return float(K[0][0])
+
+    def _ray_batch(self, H, W, K, rays, ndc, near, far, use_viewdirs, c2w_staticcam):
+        if c2w_staticcam is not None:
+            raise NotImplementedError("c2w_staticcam is a visualisation-only option of the reference")
+        if not use_viewdirs:
+            raise NotImplementedError("use_viewdirs=False is not built (all reference configs enable it)")
+        return ops.ray_prep(rays, H, W, self._focal(K), near, far, ndc), rays.shape[:-2]
+
+    @staticmethod
+    def _collect(chunks, lead):
+        keys = list(chunks[0].keys())
+        out = {}
+        for k in keys:
+            vals = [c[k] for c in chunks]
+            if not torch.is_tensor(vals[0]):
+                continue
+            v = vals[0] if len(vals) == 1 else torch.cat(vals, 0)
+            out[k] = v.reshape(list(lead) + list(v.shape[1:]))
+        return out
+
+    def render_infer(self, H, W, K, chunk, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+                     c2w_staticcam=None, use_awp=False, allkernel=0, kernelpixel=None, render_noise=True, **kwargs):
+        """[rgb, depth, acc, extras], noise_rgb_raw  (reference :679-763)."""
+        rb, lead = self._ray_batch(H, W, K, rays, ndc, near, far, use_viewdirs, c2w_staticcam)
+        rets, noises = [], []
+        for i in range(0, rb.shape[0], chunk):
+            ret, ret_noise = self.render_rays(rb[i:i + chunk], **kwargs)
+            rets.append(ret)
+            noises.append(ret_noise['rgb_map'])
+        all_ret = self._collect(rets, lead)
+        head = [all_ret.pop(k) for k in ('rgb_map', 'depth_map', 'acc_map')]
+        noise = noises[0] if len(noises) == 1 else torch.cat(noises, 0)
+        return head + [all_ret], noise
+
+    def render_train_scene(self, H, W, K, chunk, rays=None, c2w=None, ndc=True, near=0., far=1.,
+                           use_viewdirs=False, c2w_staticcam=None, use_awp=False, allkernel=0, kernelpixel=None,
+                           render_noise=True, **kwargs):
+        """[rgb, depth, acc, extras] for (warped) training rays  (reference :766-819)."""
+        rb, lead = self._ray_batch(H, W, K, rays, ndc, near, far, use_viewdirs, c2w_staticcam)
+        rets = [self.render_rays_nonoise(rb[i:i + chunk], **kwargs) for i in range(0, rb.shape[0], chunk)]
+        all_ret = self._collect(rets, lead)
+        head = [all_ret.pop(k) for k in ('rgb_map', 'depth_map', 'acc_map')]
+        return head + [all_ret]
+
+    def render_train_noise(self, H, W, K, chunk, rays=None, c2w=None, ndc=True, near=0., far=1.,
+                           use_viewdirs=False, c2w_staticcam=None, use_awp=False, allkernel=0, kernelpixel=None,
+                           render_noise=True, **kwargs):
+        """Raw noise-MLP rgb of the un-warped rays  (reference :821-866)."""
+        rb, _ = self._ray_batch(H, W, K, rays, ndc, near, far, use_viewdirs, c2w_staticcam)
+        outs = [self.render_rays_noise(rb[i:i + chunk], **kwargs)['rgb_map'] for i in range(0, rb.shape[0], chunk)]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    # ------------------------------------------------------------------------------------------
+    # dispatcher (reference :619-677)
+    # ------------------------------------------------------------------------------------------
+    def forward(self, H, W, K, chunk=1024 * 32, rays=None, rays_info=None, poses=None, allkernel=False,
+                kernel_pixel=None, consist_loss=False, Align_matrix=None, Align_mask=None, **kwargs):
+        gamma = self.tonemapping.map_type == 'gamma'
+        if self.training and not consist_loss:
+            assert rays is not None, "Please specify rays when in the training mode"
+            force_baseline = bool(kwargs['force_naive'])
+            kwargs['img_idx'] = rays_info['images_idx'].squeeze(-1)
+            use_rbk = (self.blur_kernel_net is not None and not force_baseline
+                       and self.blur_model_type == 'dpnerf')
+            if use_rbk:
+                if not self.blur_kernel_net.use_dpnerf:
+                    return None  # the reference falls through without a return here too
+                rays_transform, ccw = self.mlp_rbk(rays, rays_info)
+                Kr = ccw.shape[-1]
+                if allkernel:
+                    keep = kernel_pixel.repeat_interleave(5)[:, None, None]   # 5 is hard-coded upstream (:642)
+                    rays_transform = torch.where(keep, rays_transform, rays_transform.detach())
+                rgb, depth, acc, extras = self.render_train_scene(H, W, K, chunk, rays_transform, **kwargs)
+                noise_raw = self.render_train_noise(H, W, K, chunk, rays, **kwargs)
+                # K-ray blend + 0.1*sigmoid(noise) + gamma in one kernel per output pair (:649-654)
+                blur, pure, noise_rgb = ops.blend_tonemap(rgb, ccw, noise_raw, Kr, gamma)
+                blur0, pure0, _ = ops.blend_tonemap(extras['rgb0'], ccw, noise_raw, Kr, gamma)
+                return blur, blur0, {}, noise_rgb, noise_rgb, pure, pure0
+            (rgb, depth, acc, extras), noise_raw = self.render_infer(H, W, K, chunk, rays, **kwargs)
+            _, pure, noise_rgb = ops.blend_tonemap(rgb, None, noise_raw, 1, gamma)
+            _, pure0, _ = ops.blend_tonemap(extras['rgb0'], None, None, 1, gamma)
+            return pure, pure0, {}, noise_rgb, noise_rgb, {}, {}
+        if self.training and consist_loss:
+            kwargs['render_kwargs'].pop('save_warped_ray_img', False)
+            return self.Render_Aligned_Pixel(H, W, K, chunk, poses, images_idx=rays_info,
+                                             align_matrix=Align_matrix, align_mask=Align_mask, **kwargs)
+        kwargs['render_kwargs'].pop('save_warped_ray_img', False)
+        assert poses is not None, "Please specify poses when in the eval model"
+        rgbs, rgbs_noise, depths = self.render_path(H, W, K, chunk, poses, **kwargs)
+        P, Hh, Ww = rgbs.shape[0], rgbs.shape[1], rgbs.shape[2]
+        _, rgbs_tm, nz = ops.blend_tonemap(rgbs.reshape(-1, 3), None, rgbs_noise.reshape(-1, 3), 1, gamma)
+        # the reference tone-maps the noise image as well: tm(0.1*sigmoid(noise))  (:675-677)
+        _, nz_tm, _ = ops.blend_tonemap(nz, None, None, 1, gamma)
+        return rgbs_tm.reshape(P, Hh, Ww, 3), nz_tm.reshape(-1, Hh, Ww, 3), depths
+
+    # ------------------------------------------------------------------------------------------
+    # image rendering (reference :868-896)
+    # ------------------------------------------------------------------------------------------
+    def render_path(self, H, W, K, chunk, render_poses, render_kwargs, render_factor=0):
+        if render_factor != 0:
+            H, W = H // render_factor, W // render_factor
+        rgbs, depths, noises = [], [], []
+        t = time.time()
+        verbose = os.environ.get("LUSH_VERBOSE", "1") != "0"
+        for i, c2w in enumerate(render_poses):
+            if verbose:
+                print(i, time.time() - t)
+            t = time.time()
+            rays = torch.stack(get_rays(H, W, K, c2w), dim=-1)
+            (rgb, depth, acc, extras), rgb_noise = self.render_infer(H, W, K, chunk=chunk, rays=rays,
+                                                                    c2w=c2w[:3, :4], **render_kwargs)
+            rgbs.append(rgb)
+            noises.append(rgb_noise)
+            depths.append(depth)
+            if i == 0 and verbose:
+                print(rgb.shape, rgb_noise.shape)
+        return torch.stack(rgbs, 0), torch.stack(noises, 0), torch.stack(depths, 0)
+
+    def Render_Aligned_Pixel(self, H, W, K, chunk, render_poses, images_idx, render_kwargs, render_factor=0,
+                             align_matrix=None, align_mask=None):
+        """Stage-3 consistency rays (reference :949-988): 32 matched pixels per training view, rendered
+        through the scene branch only."""
+        if render_factor != 0:
+            H, W = H // render_factor, W // render_factor
+        dev = render_poses.device
+        anchor = random.randint(0, len(render_poses) - 1)
+        samples = torch.as_tensor(np.random.randint(0, 640 * 1120, size=32), device=dev).long()
+        anchor_pose = align_matrix[anchor][:, samples]
+        anchor_certain = align_mask[anchor][:, samples]
+        V = len(render_poses)
+        rgb_align = torch.zeros([V, 32, 3], device=dev)
+        certain_align = torch.zeros([V, 32], device=dev)
+        for i in range(V):
+            c2w = render_poses[i]
+            rays = torch.stack(get_rays(H, W, K, c2w), dim=-1).reshape(H, W, 3, 2)
+            px = anchor_pose[i, :, 2:].long()
+            rays = rays[torch.clamp(px[:, 1], 0, H - 1), torch.clamp(px[:, 0], 0, W - 1)].reshape(-1, 3, 2)
+            rgb, _, _, _ = self.render_train_scene(H, W, K, chunk=chunk, rays=rays.detach(), c2w=c2w[:3, :4],
+                                                   render_noise=False, **render_kwargs)
+            rgb_align[i] = rgb
+            certain_align[i] = anchor_certain[i]
+        return rgb_align, certain_align

@@ -1,0 +1,327 @@
+"""torch.autograd.Function wrappers over the C ABI (include/lushnerf_b200.h).
+
+PyTorch is plumbing here: it owns device memory (caching allocator), the current stream and the autograd
+tape.  Every numerical step of the hot path is one of the hand-written sm_100a kernels in csrc/.
+"""
+from __future__ import annotations
+
+import os
+from ctypes import byref, c_void_p
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import MlpDesc, check, lib, ptr, stream
+
+# MLP implementation: 1 = tcgen05 fp16-operand / fp32-accumulate (default when the topology is covered),
+# 0 = exact fp32 SIMT (strict-parity mode).  LUSH_MLP_IMPL=simt|tc overrides the default.
+_IMPL_ENV = {"simt": 0, "fp32": 0, "0": 0, "tc": 1, "tcgen05": 1, "1": 1}
+
+
+def default_mlp_impl() -> int:
+    return _IMPL_ENV.get(os.environ.get("LUSH_MLP_IMPL", "tc").lower(), 1)
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _empty(shape, like):
+    return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# ray preparation (reference models/lushnerf.py:706-729, helpers:542-562)
+# ------------------------------------------------------------------------------------------------
+class _RayPrep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays, H, W, focal, near, far, ndc):
+        rays = _f32c(rays)
+        R = rays.shape[0]
+        out = _empty((R, 11), rays)
+        check(lib().lush_ray_prep_fwd(ptr(rays, "rays"), ptr(out), R, int(H), int(W), float(focal),
+                                      float(near), float(far), int(bool(ndc)), stream()), "lush_ray_prep_fwd")
+        ctx.save_for_backward(rays)
+        ctx.meta = (int(H), int(W), float(focal), int(bool(ndc)))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (rays,) = ctx.saved_tensors
+        H, W, focal, ndc = ctx.meta
+        g = _f32c(g)
+        g_rays = torch.empty_like(rays)
+        check(lib().lush_ray_prep_bwd(ptr(rays), ptr(g), ptr(g_rays), rays.shape[0], H, W, focal, ndc,
+                                      stream()), "lush_ray_prep_bwd")
+        return g_rays, None, None, None, None, None, None
+
+
+def ray_prep(rays: torch.Tensor, H: int, W: int, focal: float, near=0.0, far=1.0, ndc=True) -> torch.Tensor:
+    """rays [..., 3, 2] -> ray_batch [R, 11] = (o, d, near, far, viewdirs)."""
+    return _RayPrep.apply(rays.reshape(-1, 3, 2), H, W, focal, near, far, ndc)
+
+
+# ------------------------------------------------------------------------------------------------
+# coarse sample placement (reference models/lushnerf.py:389-412)
+# ------------------------------------------------------------------------------------------------
+_LINSPACE_CACHE = {}
+
+
+def linspace01(n: int, device) -> torch.Tensor:
+    """torch.linspace(0, 1, n) evaluated on the CPU (the oracle's device) and cached on `device`."""
+    key = (int(n), str(device))
+    t = _LINSPACE_CACHE.get(key)
+    if t is None:
+        t = torch.linspace(0.0, 1.0, steps=int(n)).to(device)
+        _LINSPACE_CACHE[key] = t
+    return t
+
+
+@torch.no_grad()
+def stratified_z(ray_batch: torch.Tensor, t_vals: torch.Tensor, t_rand: Optional[torch.Tensor] = None,
+                 lindisp: bool = False) -> torch.Tensor:
+    """z [R, S]; near/far are read from columns 6, 7 of ray_batch.  No gradient (near/far are constants)."""
+    rb = _f32c(ray_batch.detach())
+    R, S = rb.shape[0], t_vals.shape[0]
+    z = _empty((R, S), rb)
+    check(lib().lush_stratified_z(ptr(rb), rb.shape[1], ptr(_f32c(t_vals)), ptr(_f32c(t_rand)), ptr(z), R, S,
+                                  int(bool(lindisp)), stream()), "lush_stratified_z")
+    return z
+
+
+# ------------------------------------------------------------------------------------------------
+# alpha compositing (reference models/lushnerf.py:296-352)
+# ------------------------------------------------------------------------------------------------
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, z, rays_d, sigma_noise, thresh, white_bkgd, flags):
+        raw, z, sigma_noise = _f32c(raw), _f32c(z), _f32c(sigma_noise)
+        if rays_d.dtype != torch.float32 or rays_d.stride(-1) != 1:
+            rays_d = rays_d.float().contiguous()
+        R, S = z.shape
+        d_stride = rays_d.stride(0) if R > 1 else max(3, rays_d.stride(0))
+        rgb, dens = _empty((R, 3), raw), _empty((R, max(S - 1, 0)), raw)
+        acc, w, depth = _empty((R,), raw), _empty((R, S), raw), _empty((R,), raw)
+        fptr = c_void_p(flags.data_ptr()) if flags is not None else None
+        check(lib().lush_composite_fwd(ptr(raw, "raw"), ptr(z, "z"), c_void_p(rays_d.data_ptr()), d_stride,
+                                       ptr(sigma_noise), float(thresh), int(bool(white_bkgd)), ptr(rgb),
+                                       ptr(dens), ptr(acc), ptr(w), ptr(depth), fptr, R, S, stream()),
+              "lush_composite_fwd")
+        ctx.save_for_backward(raw, z, rays_d, sigma_noise)
+        ctx.meta = (float(thresh), int(bool(white_bkgd)), d_stride)
+        return rgb, dens, acc, w, depth
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_dens, g_acc, g_w, g_depth):
+        raw, z, rays_d, sigma_noise = ctx.saved_tensors
+        thresh, white, d_stride = ctx.meta
+        R, S = z.shape
+        g_raw = torch.empty_like(raw)
+        need_d = ctx.needs_input_grad[2]
+        g_d = _empty((R, 3), raw) if need_d else None
+        check(lib().lush_composite_bwd(ptr(raw), ptr(z), c_void_p(rays_d.data_ptr()), d_stride,
+                                       ptr(sigma_noise), thresh, white, ptr(_f32c(g_rgb)), ptr(_f32c(g_dens)),
+                                       ptr(_f32c(g_acc)), ptr(_f32c(g_w)), ptr(_f32c(g_depth)), ptr(g_raw),
+                                       ptr(g_d), R, S, stream()), "lush_composite_bwd")
+        return g_raw, None, g_d, None, None, None, None
+
+
+def composite(raw, z, rays_d, sigma_noise=None, rm_near_thresh: float = -1.0, white_bkgd=False, flags=None):
+    """raw2outputs: returns (rgb_map, density, acc, weights, depth).  rays_d may be a strided [R,3] view
+    (e.g. ray_batch[:, 3:6]).  z carries no gradient (the reference's z is built from constants)."""
+    if not raw.is_cuda:
+        raise RuntimeError("lush_nerf_b200.composite needs CUDA tensors; there is no CPU fallback")
+    return _Composite.apply(raw, z.detach(), rays_d, None if sigma_noise is None else sigma_noise.detach(),
+                            rm_near_thresh, white_bkgd, flags)
+
+
+# ------------------------------------------------------------------------------------------------
+# hierarchical sampling (reference helpers:566-609; models/lushnerf.py:435-440,465)
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def sample_pdf_cuda(bins, weights, u, cdf: Optional[torch.Tensor] = None, return_inds=False):
+    bins, weights, u = _f32c(bins), _f32c(weights), _f32c(u)
+    R, nb = bins.shape
+    N = u.shape[-1]
+    u_stride = 0 if u.dim() == 1 else N
+    samples = _empty((R, N), bins)
+    inds = torch.empty((R, N), dtype=torch.int64, device=bins.device) if return_inds else None
+    check(lib().lush_sample_pdf(ptr(bins, "bins"), ptr(weights, "weights"), ptr(_f32c(cdf)), ptr(u, "u"),
+                                u_stride, ptr(samples), ptr(inds, dtype=torch.int64), R, nb, N, stream()),
+          "lush_sample_pdf")
+    return (samples, inds) if return_inds else samples
+
+
+@torch.no_grad()
+def sample_merge(z, weights, u, want_std=True):
+    """Fused z_mid + sample_pdf(weights[:,1:-1]) + sort(cat(z, samples)) + z_std."""
+    z, weights, u = _f32c(z), _f32c(weights), _f32c(u)
+    R, S = z.shape
+    N = u.shape[-1]
+    u_stride = 0 if u.dim() == 1 else N
+    z_fine, z_samples = _empty((R, S + N), z), _empty((R, N), z)
+    z_std = _empty((R,), z) if want_std else None
+    check(lib().lush_sample_merge(ptr(z, "z"), ptr(weights, "weights"), ptr(u, "u"), u_stride, ptr(z_fine),
+                                  ptr(z_samples), ptr(z_std), R, S, N, stream()), "lush_sample_merge")
+    return z_fine, z_samples, z_std
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder + MLP (reference helpers:311-344, 394-423, 483-512; models/lushnerf.py:234-293)
+# ------------------------------------------------------------------------------------------------
+# bench.py sets this to a list to collect (start, end) CUDA-event pairs around every MLP launch sequence
+MLP_EVENT_SINK = None
+
+
+class _Timed:
+    def __enter__(self):
+        self.on = MLP_EVENT_SINK is not None
+        if self.on:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record()
+            MLP_EVENT_SINK.append((self.a, self.b))
+
+
+def mlp_impl_supported(desc: MlpDesc, impl: int) -> bool:
+    return bool(lib().lush_mlp_impl_supported(byref(desc), int(impl)))
+
+
+class _MLP(torch.autograd.Function):
+    """out[R,S,C] = net(encode(o + d*z), encode(viewdirs)).  `flat` is the flat fp32 parameter buffer
+    the individual nn.Parameters are views of; the parameters themselves are passed only so that
+    autograd routes their gradients (returned as views of one flat gradient buffer)."""
+
+    @staticmethod
+    def forward(ctx, ray_batch, z, desc, impl, flat, numels, *params):
+        rb, z = _f32c(ray_batch), _f32c(z)
+        R, S = z.shape
+        C = 4 if desc.out_mode == 0 else 3
+        out = _empty((R, S, C), rb)
+        L = lib()
+        training = any(ctx.needs_input_grad)  # grad mode is off inside forward(); this is the right test
+        stash = None
+        if training:
+            nb = L.lush_mlp_stash_bytes(byref(desc), R, S, impl)
+            stash = torch.empty((nb + 3) // 4, dtype=torch.float32, device=rb.device)
+        wb = L.lush_mlp_workspace_bytes(byref(desc), R, S, impl, 0)
+        ws = torch.empty((wb + 3) // 4, dtype=torch.float32, device=rb.device) if wb else None
+        with _Timed():
+            check(L.lush_mlp_fwd(byref(desc), ptr(flat, "params"), ptr(rb, "ray_batch"), rb.shape[1], ptr(z, "z"),
+                                 ptr(out), ptr(stash), ptr(ws), wb, R, S, impl, stream()), "lush_mlp_fwd")
+        if training:
+            ctx.save_for_backward(rb, z, flat, stash)
+            ctx.meta = (desc, impl, numels, [tuple(p.shape) for p in params])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        rb, z, flat, stash = ctx.saved_tensors
+        desc, impl, numels, shapes = ctx.meta
+        R, S = z.shape
+        L = lib()
+        g_out = _f32c(g_out)
+        g_flat = torch.zeros_like(flat)
+        g_rb = _empty((R, 11), rb) if ctx.needs_input_grad[0] else None
+        wb = L.lush_mlp_workspace_bytes(byref(desc), R, S, impl, 1)
+        ws = torch.empty((wb + 3) // 4, dtype=torch.float32, device=rb.device) if wb else None
+        with _Timed():
+            check(L.lush_mlp_bwd(byref(desc), ptr(flat), ptr(rb), rb.shape[1], ptr(z), ptr(g_out), ptr(stash),
+                                 ptr(g_flat), ptr(g_rb), ptr(ws), wb, R, S, impl, stream()), "lush_mlp_bwd")
+        grads, off = [], 0
+        for n, shp, need in zip(numels, shapes, ctx.needs_input_grad[6:]):
+            grads.append(g_flat[off:off + n].view(shp) if need else None)
+            off += n
+        if g_rb is not None and rb.shape[1] != 11:
+            full = torch.zeros_like(rb)
+            full[:, :11] = g_rb
+            g_rb = full
+        return (g_rb, None, None, None, None, None, *grads)
+
+
+def mlp_apply(ray_batch, z, desc: MlpDesc, impl: int, flat: torch.Tensor, params):
+    if not ray_batch.is_cuda:
+        raise RuntimeError("lush_nerf_b200 MLP needs CUDA tensors; there is no CPU fallback")
+    numels = [p.numel() for p in params]
+    return _MLP.apply(ray_batch, z.detach(), desc, int(impl), flat, numels, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# rigid-warp blur kernel (reference models/lushnerf.py:75-98; utils/rigid_warping.py:20-140)
+# ------------------------------------------------------------------------------------------------
+class _RbkWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays, r, v):
+        rays, r, v = _f32c(rays), _f32c(r), _f32c(v)
+        N, M = rays.shape[0], r.shape[-1]
+        out = _empty((N, M + 1, 3, 2), rays)
+        check(lib().lush_rbk_warp_fwd(ptr(rays, "rays"), ptr(r, "r"), ptr(v, "v"), ptr(out), N, M, stream()),
+              "lush_rbk_warp_fwd")
+        ctx.save_for_backward(rays, r, v)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rays, r, v = ctx.saved_tensors
+        N, M = rays.shape[0], r.shape[-1]
+        g = _f32c(g)
+        g_rays, g_r, g_v = torch.empty_like(rays), torch.empty_like(r), torch.empty_like(v)
+        check(lib().lush_rbk_warp_bwd(ptr(rays), ptr(r), ptr(v), ptr(g), ptr(g_rays), ptr(g_r), ptr(g_v), N, M,
+                                      stream()), "lush_rbk_warp_bwd")
+        return g_rays, g_r, g_v
+
+
+def rbk_warp(rays, r, v):
+    """rays [N,3,2]; r, v [N,3,M] -> [N, M+1, 3, 2] (slot 0 = the original ray)."""
+    if not rays.is_cuda:
+        raise RuntimeError("lush_nerf_b200.rbk_warp needs CUDA tensors; there is no CPU fallback")
+    return _RbkWarp.apply(rays, r, v)
+
+
+# ------------------------------------------------------------------------------------------------
+# K-ray blend + noise + tone map (reference models/lushnerf.py:100-116, 649-654; helpers:164-174)
+# ------------------------------------------------------------------------------------------------
+class _BlendTonemap(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, ccw, noise_raw, K, gamma):
+        rgb, ccw, noise_raw = _f32c(rgb), _f32c(ccw), _f32c(noise_raw)
+        N = rgb.shape[0] // K
+        blur, pure = _empty((N, 3), rgb), _empty((N, 3), rgb)
+        nz = _empty((N, 3), rgb) if noise_raw is not None else None
+        check(lib().lush_blend_tonemap_fwd(ptr(rgb, "rgb"), ptr(ccw), ptr(noise_raw), ptr(blur), ptr(pure),
+                                           ptr(nz), N, K, int(bool(gamma)), stream()), "lush_blend_tonemap_fwd")
+        ctx.save_for_backward(rgb, ccw, noise_raw)
+        ctx.meta = (N, K, int(bool(gamma)))
+        if nz is None:
+            nz = torch.zeros_like(blur)
+            ctx.mark_non_differentiable(nz)
+        return blur, pure, nz
+
+    @staticmethod
+    def backward(ctx, g_blur, g_pure, g_nz):
+        rgb, ccw, noise_raw = ctx.saved_tensors
+        N, K, gamma = ctx.meta
+        g_rgb = torch.empty_like(rgb)
+        g_ccw = torch.empty_like(ccw) if ccw is not None else None
+        g_nr = torch.empty_like(noise_raw) if noise_raw is not None else None
+        check(lib().lush_blend_tonemap_bwd(ptr(rgb), ptr(ccw), ptr(noise_raw), ptr(_f32c(g_blur)),
+                                           ptr(_f32c(g_pure)), ptr(_f32c(g_nz)) if noise_raw is not None else None,
+                                           ptr(g_rgb), ptr(g_ccw), ptr(g_nr), N, K, gamma, stream()),
+              "lush_blend_tonemap_bwd")
+        return g_rgb, g_ccw, g_nr, None, None
+
+
+def blend_tonemap(rgb, ccw=None, noise_raw=None, K: int = 1, gamma: bool = True):
+    """Returns (tm(blend + 0.1*sigmoid(noise)), tm(blend), 0.1*sigmoid(noise))."""
+    if not rgb.is_cuda:
+        raise RuntimeError("lush_nerf_b200.blend_tonemap needs CUDA tensors; there is no CPU fallback")
+    return _BlendTonemap.apply(rgb.reshape(-1, 3), ccw, noise_raw, int(K), gamma)

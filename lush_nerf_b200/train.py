@@ -1,0 +1,102 @@
+"""Ray-sharded training step: one process per GPU, every rank renders its own slice of the global ray
+batch, ONE all-reduce of the flat fp32 gradient per step over NCCL (NVLink 5 / NVSwitch), identical Adam
+on every rank.  This is the B200 replacement of the reference's nn.DataParallel wrap
+(run_lushnerf.py:348) plus its loss / optimiser lines (:652-685); SURVEY.md 8e.
+
+The path shards with no data-path collective: rays are independent, the only exchange is the sum of the
+1.30 M parameter gradients (5.2 MB).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def lush_loss(rgb_blur, rgb0_blur, target):
+    """0.5*MSE + 0.5*L1 on the fine and coarse outputs (reference run_lushnerf.py:652-661, stage 1/2)."""
+    d, d0 = rgb_blur - target, rgb0_blur - target
+    return 0.5 * (d * d).mean() + 0.5 * d.abs().mean() + 0.5 * (d0 * d0).mean() + 0.5 * d0.abs().mean()
+
+
+def shard_rows(n: int, rank: int, world: int):
+    """Rows [lo, hi) of a global batch owned by `rank` -- the same contiguous dim-0 split DataParallel's
+    scatter performs.  n must divide evenly so that the mean of local means is the global mean."""
+    if n % world:
+        raise ValueError(f"global batch {n} is not divisible by world size {world}")
+    per = n // world
+    return rank * per, (rank + 1) * per
+
+
+class FlatGradAllReduce:
+    """Packs the gradients of `params` into one flat fp32 buffer, all-reduces it once, unpacks."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = None
+
+    def __call__(self):
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        dev = self.params[0].device
+        if self.flat is None or self.flat.device != dev:
+            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:  # parameters without a gradient (NeRF_Noise.alpha_linear) contribute zeros
+            n = p.numel()
+            if p.grad is None:
+                self.flat[off:off + n].zero_()
+            else:
+                self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.div_(dist.get_world_size(self.group))
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is not None:
+                p.grad.copy_(self.flat[off:off + n].view_as(p.grad))
+            off += n
+
+
+class Trainer:
+    """model: NeRFAll (training mode).  step() = forward + loss + backward + grad all-reduce + Adam."""
+
+    def __init__(self, model, H, W, K, lrate=5e-4, render_kwargs=None, group=None, fused_adam=True):
+        self.model, self.H, self.W, self.K = model, H, W, K
+        seen, params = set(), []
+        for p in model.parameters():
+            if id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+        noise = list(model.mlp_noise_coarse.parameters())
+        noise_ids = {id(p) for p in noise}
+        base = [p for p in params if id(p) not in noise_ids]
+        kw = dict(lr=lrate)
+        if fused_adam and params[0].is_cuda:
+            kw["fused"] = True
+        # two parameter groups like the reference (run_lushnerf.py:359-371)
+        self.optimizer = torch.optim.Adam([{"params": base}, {"params": noise, "lr": lrate}], **kw)
+        self.allreduce = FlatGradAllReduce(params, group)
+        self.render_kwargs = render_kwargs or {}
+        self.lrate, self.global_step = lrate, 0
+
+    def step(self, batch, force_naive=False, allkernel=True, chunk=1024 * 32):
+        m = self.model
+        m.train()
+        out = m(self.H, self.W, self.K, chunk=chunk, rays=batch["rays"],
+                rays_info={"images_idx": batch["images_idx"]}, retraw=True, force_naive=force_naive,
+                allkernel=allkernel, kernel_pixel=batch["fq_mask"], **self.render_kwargs)
+        loss = lush_loss(out[0], out[1], batch["rgbsf"])
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        self.allreduce()
+        self.optimizer.step()
+        self.global_step += 1
+        return loss
+
+    def set_lr(self, decay_steps=250000, decay_rate=0.1):
+        lr = self.lrate * (decay_rate ** (self.global_step / decay_steps))  # reference :681-685
+        for g in self.optimizer.param_groups:
+            g["lr"] = lr

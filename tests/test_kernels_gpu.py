@@ -1,0 +1,356 @@
+"""GPU parity tests: every CUDA kernel, called through the C ABI (ctypes), against the CPU oracle and
+the golden vectors generated from the reference.  Tolerances are written next to each check:
+  * sample_pdf indices / samples (given the same cdf): bit-exact
+  * fp32 scan / elementwise kernels: 2e-6 abs on O(1) quantities (different association order)
+  * fp32 SIMT MLP: 2e-5 abs on O(1..30) raw outputs (FFMA accumulation order vs MKL)
+"""
+import numpy as np
+import pytest
+import torch
+
+from lush_nerf_b200 import _lib, ops
+from oracle import lush_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NAMES = ("rgb", "density", "acc", "weights", "depth")
+
+
+def close(a, b, tol, what=""):
+    a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.numel():
+        d = (a - b).abs().max().item()
+        assert d <= tol, f"{what}: max|diff| {d:.3e} > {tol:g}"
+
+
+def rel_l2(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ composite
+def peaky_case(R, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    raw = torch.randn(R, S, 4, generator=g)
+    raw[..., 3] = torch.relu(3 * torch.randn(R, S, generator=g)) * 5
+    z = torch.linspace(0, 1, S).expand(R, S) + torch.rand(R, S, generator=g) * (0.5 / S)
+    rd = torch.randn(R, 3, generator=g)
+    noise = torch.randn(R, S - 1, generator=g)
+    return raw, z.contiguous(), rd, noise
+
+
+@pytest.mark.parametrize("mode,thresh", [("train", -1.0), ("eval", 80 / 128)])
+def test_composite_kat1(golden, mode, thresh):
+    out = ops.composite(golden["kat1/raw"].to(DEV), golden["kat1/z"].to(DEV), golden["kat1/rays_d"].to(DEV), None, thresh)
+    for n, t in zip(NAMES, out):
+        close(t, golden[f"kat1/{mode}/{n}"], 1e-6, n)
+
+
+def test_composite_golden_fwd_bwd(golden):
+    raw = golden["r2o/raw"].to(DEV).requires_grad_(True)
+    rd = golden["r2o/rays_d"].to(DEV).requires_grad_(True)
+    outs = ops.composite(raw, golden["r2o/z"].to(DEV), rd, golden["r2o/noise"].to(DEV))
+    for n, t in zip(NAMES, outs):
+        close(t, golden[f"r2o/train/{n}"], 2e-6, n)
+    sum((o * golden[f"r2o/cot/{n}"].to(DEV)).sum() for n, o in zip(NAMES, outs)).backward()
+    close(raw.grad, golden["r2o/train/g_raw"], 2e-5, "g_raw")
+    close(rd.grad, golden["r2o/train/g_rays_d"], 2e-5, "g_rays_d")
+    outs = ops.composite(golden["r2o/raw"].to(DEV), golden["r2o/z"].to(DEV), golden["r2o/rays_d"].to(DEV), None, 80 / 128)
+    for n, t in zip(NAMES, outs):
+        close(t, golden[f"r2o/eval/{n}"], 2e-6, n)
+
+
+@pytest.mark.parametrize("R,S", [(1, 2), (3, 17), (37, 32), (64, 33), (50, 64), (33, 128), (9, 192), (7, 256), (5, 300)])
+def test_composite_vs_oracle_shapes(R, S):
+    raw, z, rd, noise = peaky_case(R, S, 100 + S)
+    cot = [torch.randn(R, 3), torch.randn(R, S - 1), torch.randn(R), torch.randn(R, S), torch.randn(R)]
+    raw_o, rd_o = raw.clone().requires_grad_(True), rd.clone().requires_grad_(True)
+    ref = O.raw2outputs(raw_o, z, rd_o, noise)
+    sum((o * c).sum() for o, c in zip(ref, cot)).backward()
+    raw_c, rd_c = raw.to(DEV).requires_grad_(True), rd.to(DEV).requires_grad_(True)
+    out = ops.composite(raw_c, z.to(DEV), rd_c, noise.to(DEV))
+    for n, a, b in zip(NAMES, out, ref):
+        close(a, b, 3e-6 * max(1.0, b.abs().max().item()), n)
+    sum((o * c.to(DEV)).sum() for o, c in zip(out, cot)).backward()
+    assert rel_l2(raw_c.grad, raw_o.grad) < 2e-5
+    assert rel_l2(rd_c.grad, rd_o.grad) < 2e-5
+
+
+def test_composite_strided_rays_d_white_bkgd_and_flags():
+    R, S = 40, 64
+    raw, z, rd, noise = peaky_case(R, S, 7)
+    rb = torch.zeros(R, 11)
+    rb[:, 3:6] = rd
+    rb_c = rb.to(DEV)
+    flags = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = ops.composite(raw.to(DEV), z.to(DEV), rb_c[:, 3:6], None, -1.0, True, flags)
+    ref = O.raw2outputs(raw, z, rd, None, -1.0, True)
+    for n, a, b in zip(NAMES, out, ref):
+        close(a, b, 3e-6, n)
+    assert int(flags.item()) == 0
+    raw2 = raw.clone()
+    raw2[3, 5, 0] = float("nan")
+    raw2[4, 6, 3] = float("inf")
+    ops.composite(raw2.to(DEV), z.to(DEV), rb_c[:, 3:6], None, -1.0, False, flags)
+    bits = int(flags.item())
+    assert bits & 1, "rgb_map nan not flagged"
+    assert bits >> 8 & 1 and bits >> 8 & 2, "raw nan/inf not flagged"
+
+
+def test_composite_saturated_sample_gradient_is_finite_and_exact():
+    # a sample with alpha == 1 in the middle of the ray (1-alpha == 0): the division-free backward must
+    # still match autograd's cumprod backward
+    R, S = 4, 16
+    raw, z, rd, _ = peaky_case(R, S, 3)
+    raw[:, 5, 3] = 1e6
+    raw_o = raw.clone().requires_grad_(True)
+    ref = O.raw2outputs(raw_o, z, rd)
+    (ref[0].sum() + ref[4].sum()).backward()
+    raw_c = raw.to(DEV).requires_grad_(True)
+    out = ops.composite(raw_c, z.to(DEV), rd.to(DEV))
+    (out[0].sum() + out[4].sum()).backward()
+    assert torch.isfinite(raw_c.grad).all()
+    close(raw_c.grad, raw_o.grad, 2e-6, "g_raw saturated")
+
+
+def test_composite_properties_full_size():
+    """BASELINE stress size (65 536 rays x 128): weights sum to 1 (last alpha is 1), rgb in [0,1],
+    depth within [z_0, z_last], linearity of rgb_map in a per-ray colour shift is exact in expectation."""
+    R, S = 65536, 128
+    g = torch.Generator(device=DEV).manual_seed(0)
+    raw = torch.randn(R, S, 4, device=DEV, generator=g)
+    raw[..., 3] = torch.relu(3 * torch.randn(R, S, device=DEV, generator=g)) * 5
+    z = (torch.linspace(0, 1, S, device=DEV).expand(R, S) + torch.rand(R, S, device=DEV, generator=g) * (0.5 / S)).contiguous()
+    rd = torch.randn(R, 3, device=DEV, generator=g)
+    rgb, dens, acc, w, depth = ops.composite(raw, z, rd)
+    assert (acc - 1).abs().max() < 2e-5
+    assert (w >= 0).all() and (rgb >= -1e-6).all() and (rgb <= 1 + 1e-5).all()
+    assert (depth >= z[:, 0] - 1e-5).all() and (depth <= z[:, -1] + 1e-5).all()
+    assert torch.equal(dens, torch.relu(raw[:, :-1, 3]))
+    # spot-check 256 rays against the oracle
+    idx = torch.arange(0, R, R // 256)
+    ref = O.raw2outputs(raw[idx].cpu(), z[idx].cpu(), rd[idx].cpu())
+    close(rgb[idx], ref[0], 3e-6, "rgb")
+    close(w[idx], ref[3], 3e-6, "weights")
+
+
+# ------------------------------------------------------------------------------------------------ sampler
+@pytest.mark.parametrize("ci", range(4))
+def test_sample_pdf_strict_bit_exact_vs_reference(golden, ci):
+    bins, w, cdf, u = (golden[f"spdf{ci}/{k}"].to(DEV) for k in ("bins", "weights", "cdf", "u"))
+    N = u.shape[1]
+    s, inds = ops.sample_pdf_cuda(bins, w, u, cdf=cdf, return_inds=True)
+    assert torch.equal(inds.cpu(), golden[f"spdf{ci}/inds_rand"])
+    assert torch.equal(s.cpu(), golden[f"spdf{ci}/rand"])
+    ud = torch.linspace(0., 1., N).to(DEV)
+    s, inds = ops.sample_pdf_cuda(bins, w, ud, cdf=cdf, return_inds=True)
+    assert torch.equal(inds.cpu(), golden[f"spdf{ci}/inds_det"])
+    assert torch.equal(s.cpu(), golden[f"spdf{ci}/det"])
+
+
+@pytest.mark.parametrize("R,nb,N", [(64, 63, 64), (33, 31, 32), (16, 127, 128), (8, 255, 256), (5, 9, 7), (3, 2, 5), (7, 40, 100)])
+@pytest.mark.parametrize("det", [True, False])
+def test_sample_pdf_fused_cdf_bit_exact_vs_oracle_kernel_order(R, nb, N, det):
+    g = torch.Generator().manual_seed(nb * 1000 + N)
+    bins = torch.sort(torch.rand(R, nb, generator=g), -1)[0]
+    w = torch.relu(torch.randn(R, nb - 1, generator=g)) ** 3
+    u = torch.linspace(0., 1., N) if det else torch.rand(R, N, generator=g)
+    s_ref, inds_ref, _ = O.sample_pdf(bins, w, u, order="kernel")
+    s, inds = ops.sample_pdf_cuda(bins.to(DEV), w.to(DEV), u.to(DEV), return_inds=True)
+    assert torch.equal(inds.cpu(), inds_ref)
+    assert torch.equal(s.cpu(), s_ref)
+    # and it is a rounding-level change w.r.t. the reference association order
+    s_t, _, _ = O.sample_pdf(bins, w, u, order="torch")
+    close(s, s_t, 2e-5, "fused vs torch-order samples")
+
+
+def test_sample_pdf_public_signature(golden):
+    from lush_nerf_b200.utils.run_lushnerf_helpers import sample_pdf
+    s = sample_pdf(golden["kat2/bins"].to(DEV), golden["kat2/weights"].to(DEV), 6, det=True)
+    close(s, golden["kat2/det"], 1e-6, "kat2 det")
+    s = sample_pdf(golden["kat2/bins"].to(DEV), golden["kat2/weights"].to(DEV), 6, det=False, pytest=True)
+    close(s, golden["kat2/pytest"], 1e-6, "kat2 pytest")
+    torch.manual_seed(1)
+    a = sample_pdf(golden["spdf0/bins"].to(DEV), golden["spdf0/weights"].to(DEV), 64, det=False)
+    torch.manual_seed(1)
+    u = torch.rand([64, 64], device=DEV)
+    b, _, _ = O.sample_pdf(golden["spdf0/bins"], golden["spdf0/weights"], u.cpu(), order="kernel")
+    assert torch.equal(a.cpu(), b)
+
+
+@pytest.mark.parametrize("R,S,N", [(50, 64, 64), (33, 32, 32), (9, 24, 16), (4, 128, 128), (3, 256, 256), (5, 17, 40)])
+@pytest.mark.parametrize("det", [True, False])
+def test_sample_merge_vs_oracle(R, S, N, det):
+    g = torch.Generator().manual_seed(S * 7 + N)
+    z = torch.sort(torch.rand(R, S, generator=g), -1)[0]
+    w = torch.relu(torch.randn(R, S, generator=g)) ** 2
+    u = torch.linspace(0., 1., N) if det else torch.rand(R, N, generator=g)
+    z_mid = 0.5 * (z[:, 1:] + z[:, :-1])
+    s_ref, _, _ = O.sample_pdf(z_mid, w[:, 1:-1], u, order="kernel")
+    zf_ref = torch.sort(torch.cat([z, s_ref], -1), -1)[0]
+    zf, zs, zstd = ops.sample_merge(z.to(DEV), w.to(DEV), u.to(DEV))
+    assert torch.equal(zs.cpu(), s_ref)
+    assert torch.equal(zf.cpu(), zf_ref)          # sorting is exact
+    close(zstd, torch.std(s_ref, dim=-1, unbiased=False), 1e-6, "z_std")
+
+
+def test_sample_merge_sortedness_full_size():
+    R, S, N = 65536, 128, 128
+    g = torch.Generator(device=DEV).manual_seed(0)
+    z = torch.sort(torch.rand(R, S, device=DEV, generator=g), -1)[0]
+    w = torch.relu(torch.randn(R, S, device=DEV, generator=g)) ** 3
+    u = torch.rand(R, N, device=DEV, generator=g)
+    zf, zs, _ = ops.sample_merge(z, w, u)
+    assert (zf[:, 1:] >= zf[:, :-1]).all()
+    assert torch.equal(torch.sort(torch.cat([z, zs], -1), -1)[0], zf)   # same multiset as torch.sort
+    zmid_lo, zmid_hi = 0.5 * (z[:, 0] + z[:, 1]), 0.5 * (z[:, -2] + z[:, -1])
+    assert (zs >= zmid_lo[:, None] - 1e-6).all() and (zs <= zmid_hi[:, None] + 1e-6).all()
+
+
+# ------------------------------------------------------------------------------------------------ rays
+def test_ray_prep_fwd_bwd(golden):
+    H, W, f = golden["rays/HWf"].tolist()
+    rays = golden["rays/rays"]
+    r_o = rays.clone().requires_grad_(True)
+    ref = O.ray_prep(r_o, int(H), int(W), f)
+    cot = torch.randn(ref.shape)
+    (ref * cot).sum().backward()
+    r_c = rays.to(DEV).requires_grad_(True)
+    out = ops.ray_prep(r_c, int(H), int(W), f)
+    close(out[:, 0:3], golden["rays/ndc_o"], 1e-6, "ndc o vs reference")
+    close(out[:, 3:6], golden["rays/ndc_d"], 1e-6, "ndc d vs reference")
+    close(out, ref, 1e-6, "ray_batch")
+    (out * cot.to(DEV)).sum().backward()
+    assert rel_l2(r_c.grad, r_o.grad) < 1e-5
+    # no-NDC branch
+    out = ops.ray_prep(rays.to(DEV), int(H), int(W), f, 2.0, 6.0, False)
+    close(out, O.ray_prep(rays, int(H), int(W), f, 2.0, 6.0, False), 1e-6, "no ndc")
+
+
+@pytest.mark.parametrize("perturb", [False, True])
+@pytest.mark.parametrize("lindisp", [False, True])
+def test_stratified_z(perturb, lindisp):
+    R, S = 37, 64
+    rb = torch.zeros(R, 11)
+    rb[:, 6] = 2.0 if lindisp else 0.0
+    rb[:, 7] = 6.0 if lindisp else 1.0
+    t_rand = torch.rand(R, S) if perturb else None
+    ref = O.stratified_z(rb[:, 6:7], rb[:, 7:8], S, t_rand, lindisp)
+    out = ops.stratified_z(rb.to(DEV), torch.linspace(0., 1., S).to(DEV), None if t_rand is None else t_rand.to(DEV), lindisp)
+    close(out, ref, 0.0 if not lindisp else 5e-7, "z")
+
+
+def test_rbk_warp_fwd_bwd(golden, det_state):
+    _, rbk = det_state
+    rays = golden["fwd/rays"]
+    N = rays.shape[0]
+    g = torch.Generator().manual_seed(2)
+    r = (torch.randn(N, 3, 4, generator=g) * 0.05)
+    v = (torch.randn(N, 3, 4, generator=g) * 0.05)
+    r[0] = 0.0  # zero rotation: theta = 1e-10 path
+    ro, rr, vv = rays.clone().requires_grad_(True), r.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    ref = O.rbk_warp(ro, rr, vv)
+    cot = torch.randn(ref.shape, generator=g)
+    (ref * cot).sum().backward()
+    rc, rrc, vvc = rays.to(DEV).requires_grad_(True), r.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
+    out = ops.rbk_warp(rc, rrc, vvc)
+    close(out, ref, 2e-6, "new_rays")
+    (out * cot.to(DEV)).sum().backward()
+    assert rel_l2(rc.grad, ro.grad) < 1e-5
+    assert rel_l2(rrc.grad[1:], rr.grad[1:]) < 2e-4
+    assert rel_l2(vvc.grad, vv.grad) < 2e-5
+    assert torch.isfinite(rrc.grad).all()
+
+
+def test_rbk_module_matches_reference_golden(golden, det_state):
+    from tests.test_abi_cpu import make_model
+    nets, rbk = det_state
+    m = make_model()
+    m.load_state_dict(O.reference_state_dict(nets, rbk), strict=False)
+    m = m.to(DEV)
+    new, ccw = m.mlp_rbk(golden["fwd/rays"].to(DEV), {"images_idx": golden["fwd/images_idx"].to(DEV)})
+    close(new, golden["rbk/new_rays"], 3e-6, "new_rays")
+    close(ccw, golden["rbk/ccw"], 2e-6, "ccw")
+
+
+def test_blend_tonemap_fwd_bwd():
+    N, K = 33, 5
+    g = torch.Generator().manual_seed(0)
+    rgb = torch.rand(N * K, 3, generator=g)
+    ccw = torch.softmax(torch.randn(N, K, generator=g), -1)
+    nz = torch.randn(N, 3, generator=g)
+    a, b, c = (t.clone().requires_grad_(True) for t in (rgb, ccw, nz))
+    ref = O.blend_tonemap(a, b, c, K)
+    cot = [torch.randn(N, 3, generator=g) for _ in range(3)]
+    sum((o * t).sum() for o, t in zip(ref, cot)).backward()
+    ac, bc, cc = (t.to(DEV).requires_grad_(True) for t in (rgb, ccw, nz))
+    out = ops.blend_tonemap(ac, bc, cc, K, True)
+    for o, r_, n in zip(out, ref, ("blur", "pure", "noise")):
+        close(o, r_, 2e-6, n)
+    sum((o * t.to(DEV)).sum() for o, t in zip(out, cot)).backward()
+    assert rel_l2(ac.grad, a.grad) < 1e-5 and rel_l2(bc.grad, b.grad) < 1e-5 and rel_l2(cc.grad, c.grad) < 1e-5
+    # K = 1 without noise = plain tone mapping
+    out = ops.blend_tonemap(rgb.to(DEV), None, None, 1, True)
+    close(out[1], rgb ** (1 / 2.2), 2e-6, "tm")
+
+
+# ------------------------------------------------------------------------------------------------ MLP (fp32 SIMT)
+def mlp_case(net_name, R, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    rb = torch.zeros(R, 11)
+    rb[:, 0:3] = torch.rand(R, 3, generator=g) * 2 - 1
+    rb[:, 3:6] = torch.randn(R, 3, generator=g) * 0.5
+    v = torch.randn(R, 3, generator=g)
+    rb[:, 8:11] = v / v.norm(dim=-1, keepdim=True)
+    rb[:, 7] = 1
+    z = torch.sort(torch.rand(R, S, generator=g), -1)[0]
+    return rb, z
+
+
+@pytest.mark.parametrize("net_name,D,W,mode", [("coarse", 8, 256, 0), ("noise", 4, 128, 1)])
+@pytest.mark.parametrize("R,S", [(5, 7), (64, 24)])
+def test_mlp_simt_fwd_bwd_vs_oracle(det_state, net_name, D, W, mode, R, S):
+    nets, _ = det_state
+    rb, z = mlp_case(net_name, R, S, 5)
+    p = {k: t.clone().requires_grad_(True) for k, t in nets[net_name].items()}
+    rb_o = rb.clone().requires_grad_(True)
+    ref = O.mlp_on_rays(p, rb_o, z, D, W, 10, 4, 4, mode)
+    cot = torch.randn(ref.shape)
+    (ref * cot).sum().backward()
+    desc = _lib.MlpDesc(D, W, 10, 4, 4, mode)
+    params = [t.clone().to(DEV) for _, t in ((n, nets[net_name][n]) for n, _ in O.mlp_param_shapes(D, W, 63, 27, 4))]
+    flat = torch.cat([t.reshape(-1) for t in params])
+    views, off = [], 0
+    for t in params:
+        views.append(flat[off:off + t.numel()].view(t.shape).requires_grad_(True))
+        off += t.numel()
+    rb_c = rb.to(DEV).requires_grad_(True)
+    out = ops.mlp_apply(rb_c, z.to(DEV), desc, 0, flat, views)
+    close(out, ref, 3e-5 * max(1.0, ref.abs().max().item()), "mlp out")
+    # inference path (no stash, chunked workspace) gives the same numbers
+    with torch.no_grad():
+        out2 = ops.mlp_apply(rb.to(DEV), z.to(DEV), desc, 0, flat, [v.detach() for v in views])
+    close(out2, out, 1e-6, "inference == training forward")
+    (out * cot.to(DEV)).sum().backward()
+    for (name, _), v in zip(O.mlp_param_shapes(D, W, 63, 27, 4), views):
+        gref = p[name].grad
+        if gref is None:  # noise MLP: alpha_linear never receives a gradient
+            assert v.grad is None or float(v.grad.abs().max()) == 0.0
+            continue
+        assert rel_l2(v.grad, gref) < 2e-5, name
+    g_c, g_o = rb_c.grad.cpu(), rb_o.grad
+    assert rel_l2(g_c[:, 0:6], g_o[:, 0:6]) < 5e-5
+    assert rel_l2(g_c[:, 8:11], g_o[:, 8:11]) < 5e-5
+
+
+def test_mlp_golden_outputs_through_public_mlpforward(golden, det_state):
+    from tests.test_abi_cpu import make_model
+    nets, rbk = det_state
+    m = make_model()
+    m.load_state_dict(O.reference_state_dict(nets, rbk), strict=False)
+    m = m.to(DEV)
+    m.mlp_coarse.mlp_impl = 0
+    pts, views = golden["mlp/pts"].to(DEV), golden["mlp/views"].to(DEV)
+    out = m.mlpforward(pts[:, None, :], views, m.mlp_coarse)
+    close(out[:, 0, :], golden["mlp/coarse/out"], 5e-5, "NeRF.forward golden")

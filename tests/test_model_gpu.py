@@ -1,0 +1,170 @@
+"""GPU end-to-end parity of the drop-in surface (NeRFAll / render_rays / forward) against the golden
+vectors produced by the reference and against the CPU oracle on identical seeded inputs.
+
+Tolerances (fp32 SIMT MLP mode, `mlp_impl = 0`): ray-level outputs 2e-5 abs (values O(1)), gradients 1e-4
+relative L2.  The tcgen05 fp16-operand mode is checked against the north_star bar (max-abs 1e-3 on rgb) in
+tests/test_mlp_tc_gpu.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lush_oracle as O
+from tests.test_abi_cpu import make_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+KW = dict(retraw=True, perturb=1.0, N_importance=16, N_samples=24, use_viewdirs=True, white_bkgd=False,
+          raw_noise_std=1.0, inference=False, near=0.0, far=1.0)
+
+
+def close(a, b, tol, what=""):
+    a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    d = (a - b).abs().max().item()
+    assert d <= tol, f"{what}: max|diff| {d:.3e} > {tol:g}"
+
+
+def build(det_state, impl=0):
+    nets, rbk = det_state
+    m = make_model(N_importance=16, N_samples=24)
+    m.load_state_dict(O.reference_state_dict(nets, rbk), strict=False)
+    m = m.to(DEV)
+    for net in (m.mlp_coarse, m.mlp_fine, m.mlp_noise_coarse):
+        net.mlp_impl = impl
+    return m
+
+
+def inject(model, draws):
+    q = [d.to(DEV) for d in draws]
+
+    def fn(kind, shape, device):
+        t = q.pop(0)
+        assert list(t.shape) == list(shape), (kind, shape, t.shape)
+        return t
+    model.rng_override = fn
+
+
+def K_of(golden):
+    H, W, f = golden["rays/HWf"].tolist()
+    return int(H), int(W), np.array([[f, 0, 0.5 * W], [0, f, 0.5 * H], [0, 0, 1]])
+
+
+KEYS = ("rgb_map", "depth_map", "acc_map", "rgb0", "depth0", "acc0", "z_std")
+
+
+def test_render_rays_eval_vs_reference_golden(golden, det_state):
+    m = build(det_state).eval()
+    H, W, K = K_of(golden)
+    from lush_nerf_b200 import ops
+    rb = ops.ray_prep(golden["rays/rays"].to(DEV), H, W, K[0][0])
+    with torch.no_grad():
+        ret, retn = m.render_rays(rb, 24, retraw=True, perturb=0.0, N_importance=16, raw_noise_std=0.0, inference=True)
+    for k in KEYS:
+        close(ret[k], golden[f"rr/eval/{k}"], 3e-5, k)
+    # per-sample tensors: compare where the fine z agree (rounding-level cdf differences can move a sample)
+    close(ret["density0"], golden["rr/eval/density0"], 2e-3, "density0")
+    close(retn["rgb_map"], golden["rr/eval/noise_rgb"], 2e-5, "noise rgb")
+    assert set(ret) == {"rgb_map", "depth_map", "acc_map", "density_map", "raw", "rgb0", "depth0", "acc0", "density0", "z_std"}
+    assert ret["raw"].shape == (24, 40, 4) and ret["density_map"].shape == (24, 39) and ret["density0"].shape == (24, 23)
+
+
+def test_render_rays_train_vs_reference_golden(golden, det_state):
+    m = build(det_state).train()
+    H, W, K = K_of(golden)
+    from lush_nerf_b200 import ops
+    rb = ops.ray_prep(golden["rays/rays"].to(DEV), H, W, K[0][0])
+    inject(m, [golden["rr/train/t_rand"], golden["rr/train/noise_c"], golden["rr/train/u"], golden["rr/train/noise_f"]])
+    ret, _ = m.render_rays(rb, 24, retraw=True, perturb=1.0, N_importance=16, raw_noise_std=1.0)
+    for k in KEYS:
+        close(ret[k], golden[f"rr/train/{k}"], 3e-5, k)
+
+
+@pytest.mark.parametrize("mode", ["rbk", "naive"])
+def test_forward_train_vs_reference_golden(golden, det_state, mode):
+    m = build(det_state).train()
+    H, W, K = K_of(golden)
+    inject(m, [golden[f"fwd/{mode}/{k}"] for k in ("t_rand", "noise_c", "u", "noise_f")])
+    rays = golden["fwd/rays"].to(DEV).requires_grad_(True)
+    out = m(H, W, K, chunk=1024, rays=rays, rays_info={"images_idx": golden["fwd/images_idx"].to(DEV)},
+            force_naive=(mode == "naive"), allkernel=True, kernel_pixel=golden["fwd/kernel_pixel"].to(DEV), **KW)
+    assert len(out) == 7 and out[2] == {}
+    for i in (0, 1, 3) + ((5, 6) if mode == "rbk" else ()):
+        close(out[i], golden[f"fwd/{mode}/out{i}"], 3e-5, f"out{i}")
+    if mode == "naive":
+        assert out[5] == {} and out[6] == {}
+    tgt = golden["fwd/target"].to(DEV)
+    loss = ((out[0] - tgt) ** 2).mean() + ((out[1] - tgt) ** 2).mean() + (out[0] - tgt).abs().mean() + (out[1] - tgt).abs().mean()
+    close(loss, golden[f"fwd/{mode}/loss"], 2e-5, "loss")
+    loss.backward()
+    if mode == "rbk":
+        g, gr = rays.grad.cpu(), golden["fwd/rbk/g_rays"]
+        assert ((g - gr).norm() / gr.norm()).item() < 2e-4, "d rays"
+    worst = 0.0
+    for name, p in m.named_parameters():
+        if name.startswith(("blur_kernel_net", "dbk_view_embedding")):
+            continue
+        dig = golden[f"fwd/{mode}/grad/{name}/digest"].double()
+        g = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu().reshape(-1).double()
+        head = golden[f"fwd/{mode}/grad/{name}/head"].double()
+        scale = max(dig[1].item(), 1e-12)
+        if dig[1].item() == 0.0:
+            assert g.abs().max().item() == 0.0, name
+            continue
+        assert abs(g.norm().item() - dig[1].item()) <= 2e-4 * scale, (name, g.norm().item(), dig[1].item())
+        assert (g[:8] - head).abs().max().item() <= 2e-4 * scale + 1e-9, name
+        worst = max(worst, abs(g.norm().item() - dig[1].item()) / scale)
+    print(f"[{mode}] worst relative |grad| norm deviation vs reference: {worst:.2e}")
+
+
+def test_forward_eval_vs_reference_golden(golden, det_state):
+    m = build(det_state).eval()
+    Hs, Ws = golden["eval/HW"].tolist()
+    with torch.no_grad():
+        rgbs, noise, depths = m(int(Hs), int(Ws), golden["eval/K"].numpy(), chunk=32, poses=golden["eval/poses"].to(DEV),
+                                render_kwargs=dict(perturb=False, N_importance=16, N_samples=24, use_viewdirs=True,
+                                                   white_bkgd=False, raw_noise_std=0., inference=True, near=0., far=1.))
+    close(rgbs, golden["eval/rgbs"], 3e-5, "rgbs")
+    close(noise, golden["eval/noise"], 3e-5, "noise image")
+    close(depths, golden["eval/depths"], 3e-5, "depths")
+
+
+def test_forward_rbk_seeded_vs_oracle_larger(det_state):
+    """A larger seeded case against the CPU oracle with the CUDA RNG stream replayed (same draw order and
+    shapes as the reference: rand[R,S], randn[R,S-1], rand[R,N], randn[R,S+N-1])."""
+    nets, rbk = det_state
+    m = build(det_state).train()
+    H, W, f = 40, 60, 50.0
+    K = np.array([[f, 0, 0.5 * W], [0, f, 0.5 * H], [0, 0, 1]])
+    N, S, Nf = 96, 32, 32
+    g = torch.Generator().manual_seed(1)
+    c2w = torch.tensor([[0.99, 0.02, -0.1, 0.1], [-0.02, 0.999, 0.03, -0.05], [0.1, -0.03, 0.99, 0.2]])
+    ro, rd = O.get_rays(H, W, K, c2w)
+    rays_all = torch.stack([ro, rd], -1).reshape(-1, 3, 2)
+    rays = rays_all[torch.randperm(rays_all.shape[0], generator=g)[:N]].contiguous()
+    idx = torch.randint(0, 20, (N, 1), generator=g)
+    kw = dict(KW, N_samples=S, N_importance=Nf)
+    torch.manual_seed(11)
+    out = m(H, W, K, chunk=4096, rays=rays.to(DEV), rays_info={"images_idx": idx.to(DEV)}, force_naive=False,
+            allkernel=False, kernel_pixel=None, **kw)
+    torch.manual_seed(11)
+    R = N * 5
+    t_rand = torch.rand([R, S], device=DEV).cpu()
+    noise_c = torch.randn([R, S - 1], device=DEV).cpu()
+    u = torch.rand([R, Nf], device=DEV).cpu()
+    noise_f = torch.randn([R, S + Nf - 1], device=DEV).cpu()
+    with torch.no_grad():
+        ref, _ = O.nerfall_train_forward(nets, rbk, O.POSTER_CFG, rays, idx, H, W, f, N_samples=S, N_importance=Nf,
+                                         t_rand=t_rand, noise_c=noise_c, noise_f=noise_f, u=u, sample_order="kernel")
+    for i in (0, 1, 3, 5, 6):
+        close(out[i], ref[i], 3e-5, f"out{i}")
+
+
+def test_numerical_guard_prints(det_state, capsys, monkeypatch):
+    monkeypatch.setenv("LUSH_NUMERIC_GUARD", "sync")
+    m = build(det_state).eval()
+    with torch.no_grad():
+        m.mlp_coarse.rgb_linear.bias.fill_(float("nan"))
+        rb = torch.zeros(4, 11, device=DEV)
+        rb[:, 5] = -1; rb[:, 7] = 1; rb[:, 10] = -1
+        m.render_rays(rb, 24, perturb=0.0, N_importance=16)
+    assert "! [Numerical Error] rgb_map contains nan." in capsys.readouterr().out

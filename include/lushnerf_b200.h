@@ -173,6 +173,14 @@ int lush_blend_tonemap_bwd(const float* rgb, const float* ccw, const float* nois
                            float* g_rgb, float* g_ccw, float* g_noise_raw, int64_t N, int K,
                            int gamma, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Diagnostics (not on the product path): one-CTA tcgen05 GEMM D[128,N] = A[128,K] . B[N,K]^T over fp16
+ * "tile-canonical" operand blobs, used by the GPU tests to pin the UMMA descriptor conventions that the
+ * fused MLP kernels rely on.  a_mode / b_mode: 0 = K-major view, 1 = MN-major view of the blob.
+ * ------------------------------------------------------------------------------------------- */
+int lush_tc_selftest(const void* a_blob, const void* b_blob, float* d_out, int N, int K, int a_mode,
+                     int b_mode, int swap_lbo_sbo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "lush_rbk_warp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "lush_blend_tonemap_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "lush_blend_tonemap_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "lush_tc_selftest": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
 }
 
 _lib = None

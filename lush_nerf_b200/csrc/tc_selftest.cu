@@ -1,0 +1,88 @@
+// Hardware self-test of the UMMA conventions in tc_common.cuh (not on the product path):
+// one CTA, D[128 x N] = A[128 x K] * B[N x K]^T with fp16 operands held in tile-canonical blobs,
+// in either operand-major mode.  Called from tests/test_tc_selftest_gpu.py through the C ABI.
+#include "tc_common.cuh"
+
+namespace lush {
+using namespace tc;
+
+// a_mode / b_mode: 0 = K-major view, 1 = MN-major view of the blob
+// K-major A: blob rows = 128 (M), cols = K.   MN-major A: blob rows = K, cols = 128 (M).
+// K-major B: blob rows = N, cols = K.         MN-major B: blob rows = K, cols = N.
+__global__ void __launch_bounds__(128) tc_selftest_kernel(const __half* __restrict__ a_blob,
+                                                          const __half* __restrict__ b_blob,
+                                                          float* __restrict__ d_out, int N, int K, int a_mode,
+                                                          int b_mode, int swap_lbo_sbo) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t a_bytes = 128u * K * 2u, b_bytes = (uint32_t)N * K * 2u;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + a_bytes;
+  for (uint32_t i = tid * 16; i < a_bytes; i += 128 * 16)
+    *reinterpret_cast<uint4*>(sa + i) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a_blob) + i);
+  for (uint32_t i = tid * 16; i < b_bytes; i += 128 * 16)
+    *reinterpret_cast<uint4*>(sb + i) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(b_blob) + i);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_f16(128, N, a_mode, b_mode);
+    // per K=16 step: K-major advances two 8-column groups (2*rows*16 B); MN-major advances 16 rows (256 B)
+    const uint32_t a_rows = a_mode == 0 ? 128u : (uint32_t)K;
+    const uint32_t b_rows = b_mode == 0 ? (uint32_t)N : (uint32_t)K;
+    uint32_t a_lbo = a_mode == 0 ? a_rows * 16u : 128u, a_sbo = a_mode == 0 ? 128u : a_rows * 16u;
+    uint32_t b_lbo = b_mode == 0 ? b_rows * 16u : 128u, b_sbo = b_mode == 0 ? 128u : b_rows * 16u;
+    if (swap_lbo_sbo) {
+      uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t;
+      t = b_lbo; b_lbo = b_sbo; b_sbo = t;
+    }
+    const uint32_t a_step = a_mode == 0 ? 2u * a_rows * 16u : 256u;
+    const uint32_t b_step = b_mode == 0 ? 2u * b_rows * 16u : 256u;
+    for (int k = 0; k < K / 16; ++k) {
+      uint64_t ad = make_smem_desc(smem_u32(sa) + k * a_step, a_lbo, a_sbo);
+      uint64_t bd = make_smem_desc(smem_u32(sb) + k * b_step, b_lbo, b_sbo);
+      umma_f16(tmem_base, ad, bd, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const int row = tid;  // TMEM lane = 32*(warp%4) + lane = tid for a 128-thread block
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) d_out[row * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace lush
+
+extern "C" int lush_tc_selftest(const void* a_blob, const void* b_blob, float* d_out, int N, int K, int a_mode,
+                                int b_mode, int swap_lbo_sbo, void* stream) {
+  using namespace lush;
+  LUSH_REQUIRE(a_blob && b_blob && d_out, "tc_selftest: null pointer");
+  LUSH_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K % 16 == 0, "tc_selftest: bad N/K");
+  size_t smem = (size_t)(128 + N) * K * 2;
+  LUSH_REQUIRE(smem <= 200 * 1024, "tc_selftest: operands do not fit in shared memory");
+  int rc = check_cuda(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem), "tc_selftest: smem attr");
+  if (rc) return rc;
+  tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)a_blob, (const __half*)b_blob, d_out,
+                                                             N, K, a_mode, b_mode, swap_lbo_sbo);
+  LUSH_LAUNCH_CHECK("tc_selftest");
+  return 0;
+}

@@ -73,8 +73,8 @@ def test_composite_vs_oracle_shapes(R, S):
     for n, a, b in zip(NAMES, out, ref):
         close(a, b, 3e-6 * max(1.0, b.abs().max().item()), n)
     sum((o * c.to(DEV)).sum() for o, c in zip(out, cot)).backward()
-    assert rel_l2(raw_c.grad, raw_o.grad) < 2e-5
-    assert rel_l2(rd_c.grad, rd_o.grad) < 2e-5
+    assert rel_l2(raw_c.grad, raw_o.grad) < 2e-5, ("g_raw", rel_l2(raw_c.grad, raw_o.grad))
+    assert rel_l2(rd_c.grad, rd_o.grad) < 2e-5, ("g_rays_d", rel_l2(rd_c.grad, rd_o.grad), rd_c.grad, rd_o.grad)
 
 
 def test_composite_strided_rays_d_white_bkgd_and_flags():
@@ -160,9 +160,16 @@ def test_sample_pdf_fused_cdf_bit_exact_vs_oracle_kernel_order(R, nb, N, det):
     s, inds = ops.sample_pdf_cuda(bins.to(DEV), w.to(DEV), u.to(DEV), return_inds=True)
     assert torch.equal(inds.cpu(), inds_ref)
     assert torch.equal(s.cpu(), s_ref)
-    # and it is a rounding-level change w.r.t. the reference association order
+    # and it is a rounding-level change w.r.t. the reference association order.  The one exception is
+    # u == 1.0 exactly (last det sample): cdf[-1] rounds to either side of 1.0 depending on the order, and
+    # the sample then lands anywhere inside the LAST bin -- require only that.
     s_t, _, _ = O.sample_pdf(bins, w, u, order="torch")
-    close(s, s_t, 2e-5, "fused vs torch-order samples")
+    if det:
+        close(s[:, :-1], s_t[:, :-1], 2e-5, "fused vs torch-order samples (u < 1)")
+        last = s[:, -1].cpu()
+        assert ((last >= bins[:, -2] - 1e-6) & (last <= bins[:, -1] + 1e-6)).all(), "u = 1 sample outside last bin"
+    else:
+        close(s, s_t, 2e-5, "fused vs torch-order samples")
 
 
 def test_sample_pdf_public_signature(golden):

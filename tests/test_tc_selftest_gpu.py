@@ -1,0 +1,44 @@
+"""GPU: pins the UMMA (tcgen05.mma) shared-memory descriptor conventions of csrc/tc_common.cuh on real
+hardware with a one-CTA GEMM over fp16 tile-canonical blobs, in K-major and MN-major operand modes."""
+import ctypes
+
+import pytest
+import torch
+
+from lush_nerf_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def to_blob(mat: torch.Tensor) -> torch.Tensor:
+    """[rows, cols] fp16 -> tile-canonical blob: offset(r,c) = (c/8)*(rows*16) + r*16 + (c%8)*2 bytes."""
+    rows, cols = mat.shape
+    return mat.reshape(rows, cols // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
+
+
+def run(A, B, a_mode, b_mode, swap=0):
+    """A [128,K], B [N,K] fp16 (logical).  MN-major views store the transposed matrix in the blob."""
+    N, K = B.shape
+    a_blob = to_blob(A if a_mode == 0 else A.t().contiguous()).cuda()
+    b_blob = to_blob(B if b_mode == 0 else B.t().contiguous()).cuda()
+    out = torch.full((128, N), float("nan"), device="cuda")
+    rc = _lib.lib().lush_tc_selftest(ctypes.c_void_p(a_blob.data_ptr()), ctypes.c_void_p(b_blob.data_ptr()),
+                                     ctypes.c_void_p(out.data_ptr()), N, K, a_mode, b_mode, swap, None)
+    _lib.check(rc, "lush_tc_selftest")
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+@pytest.mark.parametrize("a_mode,b_mode", [(0, 0), (1, 1), (0, 1), (1, 0)])
+@pytest.mark.parametrize("N,K", [(256, 64), (128, 32), (64, 128), (256, 256), (16, 16)])
+def test_umma_descriptor_conventions(a_mode, b_mode, N, K):
+    g = torch.Generator().manual_seed(N * 7 + K)
+    A = (torch.randn(128, K, generator=g) * 0.5).half()
+    B = (torch.randn(N, K, generator=g) * 0.5).half()
+    ref = A.float() @ B.float().t()
+    out = run(A, B, a_mode, b_mode)
+    err = (out - ref).abs().max().item()
+    if not err < 2e-3:
+        alt = run(A, B, a_mode, b_mode, swap=1)
+        err_alt = (alt - ref).abs().max().item()
+        pytest.fail(f"UMMA result wrong: max err {err:.3e} (with LBO/SBO swapped: {err_alt:.3e})")

@@ -123,7 +123,8 @@ typedef struct lush_mlp_desc {
 
 /* Number of fp32 elements in the flat parameter buffer for `desc`. */
 int64_t lush_mlp_param_count(const lush_mlp_desc* desc);
-/* 1 if `impl` (0 = fp32 SIMT, 1 = tcgen05 fp16-operand) can run this topology, else 0. */
+/* Capability bits of `impl` (0 = fp32 SIMT, 1 = tcgen05 fp16-operand) for this topology:
+ * bit 0 = forward / inference, bit 1 = training (forward with stash + backward).  0 = unsupported. */
 int lush_mlp_impl_supported(const lush_mlp_desc* desc, int impl);
 
 /* Sample-point generation is fused in: for ray r and sample s the network input is

@@ -33,6 +33,7 @@ int lush_mlp_simt_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float
                       size_t workspace_bytes, int64_t R, int S, cudaStream_t st);
 // implemented in mlp_tc.cu
 bool lush_mlp_tc_supported(const MlpLayout& L);
+bool lush_mlp_tc_training_supported();
 size_t lush_mlp_tc_stash_bytes(const MlpLayout& L, int64_t R, int S);
 size_t lush_mlp_tc_workspace_bytes(const MlpLayout& L, int64_t R, int S, int training);
 int lush_mlp_tc_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* params,
@@ -76,8 +77,8 @@ int64_t lush_mlp_param_count(const lush_mlp_desc* desc) {
 int lush_mlp_impl_supported(const lush_mlp_desc* desc, int impl) {
   MlpLayout L;
   if (!layout_ok(desc, L, "mlp_impl_supported")) return 0;
-  if (impl == 0) return 1;
-  if (impl == 1) return lush_mlp_tc_supported(L) ? 1 : 0;
+  if (impl == 0) return 3;
+  if (impl == 1) return lush_mlp_tc_supported(L) ? (lush_mlp_tc_training_supported() ? 3 : 1) : 0;
   return 0;
 }
 

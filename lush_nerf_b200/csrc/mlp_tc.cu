@@ -1,12 +1,537 @@
-// placeholder until the tcgen05 path lands (replaced below in history)
+// Fused positional-encoder + 8x256 scene MLP on the 5th-gen tensor cores (tcgen05 / TMEM), sm_100a.
+// impl = 1 of lush_mlp_fwd: fp16 operands (11-bit significand, the same as TF32) with fp32 accumulation.
+// Replaces reference helpers:311-344 (Embedder), helpers:394-423 (NeRF.forward) and
+// models/lushnerf.py:234-266 (mlpforward) for W = 256 networks.
+//
+// Forward kernel (persistent, one CTA per SM, 320 threads):
+//   warp 0      weight producer: streams the pre-packed fp16 weight K-slices (16 KB each) with 1-D bulk
+//               async copies (cp.async.bulk, the TMA engine) through a 3-stage mbarrier ring
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16) for TWO 128-row sample
+//               tiles per weight slice (halves L2 weight traffic per row), accumulators in TMEM (2 x 256 cols)
+//   warps 2-9   two epilogue warpgroups (one per tile): tcgen05.ld -> +bias -> ReLU -> fp16 -> st.shared in
+//               the UMMA operand layout, i.e. the next layer's A operand never leaves the SM.  The sigma
+//               head (256->1) and rgb head (128->3) are register dot products in the epilogues; only
+//               [M,4] fp32 goes back to HBM (plus, in training, the fp16 activation stash for backward).
+// Activations: H tile [128 x 256] fp16 (64 KB) per tile, encodings [128 x 64] (16 KB) per tile.
 #include "mlp_common.cuh"
+#include "tc_common.cuh"
+
+namespace lush {
+using namespace tc;
+
+constexpr int TW = 256;            // network width this path is built for
+constexpr int TROWS = 128;         // rows per tile (= TMEM lanes)
+constexpr int KS = 32;             // K elements per weight slice
+constexpr int NSTAGE = 3;
+constexpr int STAGE_BYTES = TW * KS * 2;          // 16 KB
+constexpr int H_BYTES = TROWS * TW * 2;           // 64 KB
+constexpr int ENC_BYTES = TROWS * 64 * 2;         // 16 KB
+constexpr int ENCV_BYTES = TROWS * 32 * 2;        // 8 KB
+constexpr int HV_BYTES = TROWS * 128 * 2;         // 32 KB
+constexpr int MAX_STEPS = kMaxDepth + 2;
+constexpr int FWD_THREADS = 320;
+
+enum FwdEpi { EPI_TRUNK = 0, EPI_FEATURE = 1, EPI_VIEWS = 2 };
+
+struct FwdStep {
+  int N;           // output width (256 or 128)
+  int nslices;     // K slices of 32
+  int enc_slices;  // leading slices read the encoding buffer (ENC), the rest read H
+  int enc_first;   // 1: encoding segment comes first (layers 0 / skip+1); 0: H first, encoding last (views)
+  int epi;         // FwdEpi
+  int bias_off;    // float offset into the smem parameter block
+  int last_trunk;  // 1: also produce sigma = h . w_alpha + b
+  int stash_slot;  // index of the H blob this step's OUTPUT occupies in the stash record (training)
+};
+
+struct FwdPlan {
+  int nsteps;
+  int D;
+  FwdStep steps[MAX_STEPS];
+  // smem parameter block (floats): biases per step, then w_alpha[256], w_rgb[3][128], b_alpha, b_rgb[3]
+  int w_alpha_off, w_rgb_off, b_head_off, nparam_floats;
+  // stash record (bytes per tile)
+  int rec_bytes, rec_encp, rec_h0, rec_feat, rec_encv, rec_hv, rec_mask, rec_maskv;
+  int64_t wstream_bytes;
+};
+
+// ------------------------------------------------------------------------------------------------
+// host: plan + weight packing
+// ------------------------------------------------------------------------------------------------
+static void make_fwd_plan(const MlpLayout& L, FwdPlan& P) {
+  P.D = L.D;
+  int n = 0, boff = 0;
+  int64_t wbytes = 0;
+  for (int i = 0; i < L.D; ++i) {
+    FwdStep& s = P.steps[n++];
+    s.N = TW; s.epi = EPI_TRUNK; s.bias_off = boff; boff += TW;
+    s.last_trunk = (i == L.D - 1);
+    s.enc_first = 1;
+    if (i == 0) { s.nslices = 2; s.enc_slices = 2; }
+    else if (L.skip >= 0 && i == L.skip + 1) { s.nslices = 2 + TW / KS; s.enc_slices = 2; }
+    else { s.nslices = TW / KS; s.enc_slices = 0; }
+    s.stash_slot = i;
+    wbytes += (int64_t)s.nslices * s.N * KS * 2;
+  }
+  { FwdStep& s = P.steps[n++];
+    s.N = TW; s.epi = EPI_FEATURE; s.bias_off = boff; boff += TW; s.last_trunk = 0;
+    s.nslices = TW / KS; s.enc_slices = 0; s.enc_first = 1; s.stash_slot = L.D;
+    wbytes += (int64_t)s.nslices * s.N * KS * 2; }
+  { FwdStep& s = P.steps[n++];
+    s.N = 128; s.epi = EPI_VIEWS; s.bias_off = boff; boff += 128; s.last_trunk = 0;
+    s.nslices = TW / KS + 1; s.enc_slices = 1; s.enc_first = 0; s.stash_slot = -1;
+    wbytes += (int64_t)s.nslices * s.N * KS * 2; }
+  P.nsteps = n;
+  P.w_alpha_off = boff; boff += TW;
+  P.w_rgb_off = boff; boff += 3 * 128;
+  P.b_head_off = boff; boff += 4;
+  P.nparam_floats = boff;
+  P.wstream_bytes = wbytes;
+  int off = 0;
+  P.rec_encp = off; off += ENC_BYTES;
+  P.rec_h0 = off; off += L.D * H_BYTES;
+  P.rec_feat = off; off += H_BYTES;
+  P.rec_encv = off; off += ENCV_BYTES;
+  P.rec_hv = off; off += HV_BYTES;
+  P.rec_mask = off; off += L.D * TROWS * 32;   // 256 relu bits per row per trunk layer
+  P.rec_maskv = off; off += TROWS * 16;        // 128 bits per row for the views layer
+  P.rec_bytes = off;
+}
+
+// One thread per packed fp16 element of the forward weight stream.
+// Step s, slice j, element (n, kk): stream offset = step_base + j*N*KS*2 + (kk/8)*(N*16) + n*16 + (kk%8)*2
+struct PackJob {
+  int64_t out_off;   // byte offset of the step in the stream
+  int64_t w_off;     // float offset of the [N, fan_in] weight in the flat params
+  int N, fan_in, nslices;
+  int enc_slices, enc_first, enc_real, enc_col0, main_col0;  // column mapping (see pack kernel)
+};
+struct PackPlan {
+  int njobs;
+  PackJob jobs[MAX_STEPS];
+};
+
+__global__ void pack_fwd_weights_kernel(const float* __restrict__ params, __half* __restrict__ stream,
+                                        PackPlan plan) {
+  const PackJob& J = plan.jobs[blockIdx.y];
+  const int64_t total = (int64_t)J.nslices * J.N * KS;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(e / (J.N * KS));
+    int rem = (int)(e - (int64_t)j * J.N * KS);
+    int kk8 = rem / (J.N * 8);          // which 8-column group inside the slice
+    int rem2 = rem - kk8 * J.N * 8;
+    int n = rem2 / 8, k8 = rem2 % 8;
+    int k = j * KS + kk8 * 8 + k8;      // K index within the step (padded, concatenated segments)
+    // map to the nn.Linear column
+    int col = -1;
+    const int enc_k = J.enc_slices * KS;
+    const int main_k = (J.nslices - J.enc_slices) * KS;
+    if (J.enc_first) {
+      if (k < enc_k) { if (k < J.enc_real) col = J.enc_col0 + k; }
+      else col = J.main_col0 + (k - enc_k);
+    } else {
+      if (k < main_k) col = J.main_col0 + k;
+      else if (k - main_k < J.enc_real) col = J.enc_col0 + (k - main_k);
+    }
+    float v = (col >= 0) ? params[J.w_off + (int64_t)n * J.fan_in + col] : 0.f;
+    stream[J.out_off / 2 + e] = __float2half_rn(v);
+  }
+}
+
+static void make_pack_plan(const MlpLayout& L, const FwdPlan& P, PackPlan& K) {
+  K.njobs = P.nsteps;
+  int64_t off = 0;
+  for (int s = 0; s < P.nsteps; ++s) {
+    const FwdStep& st = P.steps[s];
+    PackJob& J = K.jobs[s];
+    J.out_off = off;
+    J.N = st.N; J.nslices = st.nslices; J.enc_slices = st.enc_slices; J.enc_first = st.enc_first;
+    if (s < L.D) {
+      J.w_off = L.pts_w[s]; J.fan_in = L.pts_in[s];
+      J.enc_real = L.in_ch; J.enc_col0 = 0;
+      J.main_col0 = (st.enc_slices && s > 0) ? L.in_ch : 0;   // skip layer: [input | hidden] (helpers:401)
+    } else if (s == L.D) {
+      J.w_off = L.feat_w; J.fan_in = L.W; J.enc_real = 0; J.enc_col0 = 0; J.main_col0 = 0;
+    } else {
+      J.w_off = L.views_w; J.fan_in = L.W + L.in_ch_v;       // [feature | views] (helpers:409)
+      J.enc_real = L.in_ch_v; J.enc_col0 = L.W; J.main_col0 = 0;
+    }
+    off += (int64_t)st.nslices * st.N * KS * 2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+struct FwdSmem {
+  // offsets into dynamic shared memory
+  static constexpr int H0 = 0;
+  static constexpr int ENC0 = 2 * H_BYTES;
+  static constexpr int STAGE0 = ENC0 + 2 * ENC_BYTES;
+  static constexpr int PARAMS = STAGE0 + NSTAGE * STAGE_BYTES;
+};
+
+// gamma(x) for one coordinate triple into the tile-canonical [128 x 64] (or [128 x 32]) fp16 blob, row `row`.
+// channel order: [x(3), sin(2^0 x)(3), cos(2^0 x)(3), ...]; columns >= 3+6L are zero padding.
+template <int NCOL>
+__device__ __forceinline__ void encode_row_to_smem(uint8_t* blob, int row, float x0, float x1, float x2, int L) {
+  float vals[NCOL];
+#pragma unroll
+  for (int c = 0; c < NCOL; ++c) vals[c] = 0.f;
+  vals[0] = x0; vals[1] = x1; vals[2] = x2;
+  float f = 1.f;
+#pragma unroll
+  for (int l = 0; l < (NCOL - 3) / 6; ++l) {
+    if (l < L) {
+      float s0, c0, s1, c1, s2, c2;
+      sincosf(x0 * f, &s0, &c0);
+      sincosf(x1 * f, &s1, &c1);
+      sincosf(x2 * f, &s2, &c2);
+      vals[3 + 6 * l + 0] = s0; vals[3 + 6 * l + 1] = s1; vals[3 + 6 * l + 2] = s2;
+      vals[3 + 6 * l + 3] = c0; vals[3 + 6 * l + 4] = c1; vals[3 + 6 * l + 5] = c2;
+    }
+    f *= 2.f;
+  }
+#pragma unroll
+  for (int g = 0; g < NCOL / 8; ++g) {
+    uint4 q;
+    q.x = pack_h2(vals[8 * g + 0], vals[8 * g + 1]);
+    q.y = pack_h2(vals[8 * g + 2], vals[8 * g + 3]);
+    q.z = pack_h2(vals[8 * g + 4], vals[8 * g + 5]);
+    q.w = pack_h2(vals[8 * g + 6], vals[8 * g + 7]);
+    *reinterpret_cast<uint4*>(blob + g * (TROWS * 16) + row * 16) = q;
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ params_smem_src,
+                  const float* __restrict__ ray_batch, int ray_stride, const float* __restrict__ z,
+                  float* __restrict__ out, uint8_t* __restrict__ stash, int64_t M, int S, int L_pts,
+                  int L_views, FwdPlan P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], a_ready[2], d_ready[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (M + TROWS - 1) / TROWS;
+  const int64_t nsuper = (ntiles + 1) / 2;
+  float* sparams = reinterpret_cast<float*>(smem + FwdSmem::PARAMS);
+
+  for (int i = tid; i < P.nparam_floats; i += FWD_THREADS) sparams[i] = params_smem_src[i];
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&a_ready[t], 4 * 32); mbar_init(&d_ready[t], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(wstream);
+        for (int s = 0; s < P.nsteps; ++s) {
+          const uint32_t bytes = (uint32_t)P.steps[s].N * KS * 2;
+          for (int j = 0; j < P.steps[s].nslices; ++j) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            bulk_g2s(smem + FwdSmem::STAGE0 + stage * STAGE_BYTES, src, bytes, &full_bar[stage]);
+            src += bytes;
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t a_phase[2] = {0, 0};
+      const uint32_t sbase = smem_u32(smem);
+      for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
+        const int nt = (2 * st + 1 < ntiles) ? 2 : 1;
+        for (int s = 0; s < P.nsteps; ++s) {
+          const FwdStep& S_ = P.steps[s];
+          const uint32_t idesc = make_idesc_f16(TROWS, S_.N, 0, 0);
+          const uint32_t b_lbo = (uint32_t)S_.N * 16u;
+          for (int j = 0; j < S_.nslices; ++j) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            // which activation buffer / column does this slice read?
+            bool from_enc; int kcol;
+            if (S_.enc_first) { from_enc = j < S_.enc_slices; kcol = from_enc ? j * KS : (j - S_.enc_slices) * KS; }
+            else { const int mainsl = S_.nslices - S_.enc_slices; from_enc = j >= mainsl; kcol = from_enc ? (j - mainsl) * KS : j * KS; }
+            for (int t = 0; t < nt; ++t) {
+              if (j == 0) { mbar_wait(&a_ready[t], a_phase[t]); a_phase[t] ^= 1; tc_fence_after(); }
+              const uint32_t abuf = sbase + (from_enc ? FwdSmem::ENC0 + t * ENC_BYTES : FwdSmem::H0 + t * H_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < KS / 16; ++kk) {
+                const uint64_t ad = make_smem_desc(abuf + (uint32_t)((kcol + kk * 16) / 8) * (TROWS * 16u), TROWS * 16u, 128u);
+                const uint64_t bd = make_smem_desc(sbase + FwdSmem::STAGE0 + stage * STAGE_BYTES + kk * 2u * b_lbo, b_lbo, 128u);
+                umma_f16(tmem_base + t * 256, ad, bd, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&d_ready[0]);
+          if (nt > 1) umma_commit(&d_ready[1]);
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue warpgroups ===========================
+    const int t = (warp - 2) >> 2;                    // tile slot handled by this warpgroup
+    const int row = 32 * (warp & 3) + lane;           // TMEM lane == tile row
+    const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
+    uint8_t* Hb = smem + FwdSmem::H0 + t * H_BYTES;
+    uint8_t* Eb = smem + FwdSmem::ENC0 + t * ENC_BYTES;
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const int bar_id = 1 + t;
+    uint32_t d_phase = 0;
+    for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
+      const int64_t tile = 2 * st + t;
+      if (tile >= ntiles) continue;
+      const int64_t m = tile * TROWS + row;
+      const bool valid = m < M;
+      uint8_t* rec = stash ? stash + tile * (int64_t)P.rec_bytes : nullptr;
+      // ---- prologue: sample point + encodings
+      float vx = 0.f, vy = 0.f, vz = 0.f;
+      {
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+        if (valid) {
+          const int64_t r = m / S;
+          const float* rb = ray_batch + r * ray_stride;
+          const float zz = z[m];
+          x0 = __fadd_rn(rb[0], __fmul_rn(rb[3], zz));
+          x1 = __fadd_rn(rb[1], __fmul_rn(rb[4], zz));
+          x2 = __fadd_rn(rb[2], __fmul_rn(rb[5], zz));
+          vx = rb[8]; vy = rb[9]; vz = rb[10];
+        }
+        if (rec && leader) bulk_wait_read_all();       // previous tile's stash stores still read H/ENC
+        if (rec) named_bar_sync(bar_id, 128);
+        encode_row_to_smem<64>(Eb, row, x0, x1, x2, L_pts);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&a_ready[t]);
+      if (rec) {
+        named_bar_sync(bar_id, 128);
+        if (leader) { bulk_s2g(rec + P.rec_encp, Eb, ENC_BYTES); bulk_commit(); }
+      }
+      float alpha = 0.f;
+      for (int s = 0; s < P.nsteps; ++s) {
+        const FwdStep& S_ = P.steps[s];
+        const float* bias = sparams + S_.bias_off;
+        mbar_wait(&d_ready[t], d_phase); d_phase ^= 1;
+        tc_fence_after();
+        if (rec) {                                     // the H blob of the previous step is being stored
+          if (leader) bulk_wait_read_all();
+          named_bar_sync(bar_id, 128);
+        }
+        if (S_.epi == EPI_VIEWS) {
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+          const float* wr = sparams + P.w_rgb_off;
+          uint32_t mbits[4];
+#pragma unroll 1
+          for (int cc = 0; cc < 128; cc += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + tlane + t * 256 + cc, r);
+            tmem_ld_wait();
+            uint32_t mb = 0;
+            float hv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = fmaxf(__uint_as_float(r[j]) + bias[cc + j], 0.f);
+              hv[j] = v;
+              mb |= (v > 0.f ? 1u : 0u) << j;
+              c0 = fmaf(v, wr[cc + j], c0);
+              c1 = fmaf(v, wr[128 + cc + j], c1);
+              c2 = fmaf(v, wr[256 + cc + j], c2);
+            }
+            mbits[cc >> 5] = mb;
+            if (rec) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 q;
+                q.x = pack_h2(hv[8 * g + 0], hv[8 * g + 1]); q.y = pack_h2(hv[8 * g + 2], hv[8 * g + 3]);
+                q.z = pack_h2(hv[8 * g + 4], hv[8 * g + 5]); q.w = pack_h2(hv[8 * g + 6], hv[8 * g + 7]);
+                *reinterpret_cast<uint4*>(Hb + ((cc >> 3) + g) * (TROWS * 16) + row * 16) = q;
+              }
+            }
+          }
+          if (valid) {
+            const float* bh = sparams + P.b_head_off;
+            float4 o = make_float4(c0 + bh[1], c1 + bh[2], c2 + bh[3], alpha + bh[0]);
+            reinterpret_cast<float4*>(out)[m] = o;
+          }
+          if (rec) {
+            *reinterpret_cast<uint4*>(rec + P.rec_maskv + row * 16) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
+            fence_proxy_async();
+            named_bar_sync(bar_id, 128);
+            if (leader) { bulk_s2g(rec + P.rec_hv, Hb, HV_BYTES); bulk_commit(); }
+          }
+          tc_fence_before();   // orders our TMEM reads before the next tile's a_ready arrive
+        } else {
+          uint32_t mbits[8];
+#pragma unroll 1
+          for (int cc = 0; cc < TW; cc += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + tlane + t * 256 + cc, r);
+            tmem_ld_wait();
+            float v[32];
+            uint32_t mb = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r[j]) + bias[cc + j];
+              if (S_.epi == EPI_TRUNK) x = fmaxf(x, 0.f);
+              v[j] = x;
+              mb |= (x > 0.f ? 1u : 0u) << j;
+            }
+            mbits[cc >> 5] = mb;
+            if (S_.last_trunk) {
+              const float* wa = sparams + P.w_alpha_off;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) alpha = fmaf(v[j], wa[cc + j], alpha);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 q;
+              q.x = pack_h2(v[8 * g + 0], v[8 * g + 1]); q.y = pack_h2(v[8 * g + 2], v[8 * g + 3]);
+              q.z = pack_h2(v[8 * g + 4], v[8 * g + 5]); q.w = pack_h2(v[8 * g + 6], v[8 * g + 7]);
+              *reinterpret_cast<uint4*>(Hb + ((cc >> 3) + g) * (TROWS * 16) + row * 16) = q;
+            }
+          }
+          if (S_.epi == EPI_FEATURE)   // the encoding buffer is dead after the trunk: reuse it for gamma(viewdirs)
+            encode_row_to_smem<32>(Eb, row, vx, vy, vz, L_views);
+          if (S_.last_trunk) alpha = valid ? alpha : 0.f;
+          if (rec && S_.epi == EPI_TRUNK) {
+            uint4* mp = reinterpret_cast<uint4*>(rec + P.rec_mask + (s * TROWS + row) * 32);
+            mp[0] = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
+            mp[1] = make_uint4(mbits[4], mbits[5], mbits[6], mbits[7]);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&a_ready[t]);
+          if (rec) {
+            named_bar_sync(bar_id, 128);
+            if (leader) {
+              bulk_s2g(rec + P.rec_h0 + S_.stash_slot * H_BYTES, Hb, H_BYTES);
+              if (S_.epi == EPI_FEATURE) bulk_s2g(rec + P.rec_encv, Eb, ENCV_BYTES);
+              bulk_commit();
+            }
+          }
+        }
+      }
+    }
+    if (stash && leader) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static size_t fwd_smem_bytes(const FwdPlan& P) { return (size_t)FwdSmem::PARAMS + (size_t)P.nparam_floats * 4; }
+
+// gathers biases + head weights into one contiguous float block (the kernel copies it to smem)
+__global__ void gather_fwd_params_kernel(const float* __restrict__ params, float* __restrict__ dst, MlpLayout L,
+                                         FwdPlan P) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nparam_floats) return;
+  float v;
+  if (i < P.w_alpha_off) {
+    int s = 0;
+    while (s + 1 < P.nsteps && i >= P.steps[s + 1].bias_off) ++s;
+    int c = i - P.steps[s].bias_off;
+    if (s < L.D) v = params[L.pts_b[s] + c];
+    else if (s == L.D) v = params[L.feat_b + c];
+    else v = params[L.views_b + c];
+  } else if (i < P.w_rgb_off) v = params[L.alpha_w + (i - P.w_alpha_off)];
+  else if (i < P.b_head_off) v = params[L.rgb_w + (i - P.w_rgb_off)];
+  else {
+    int c = i - P.b_head_off;
+    v = (c == 0) ? params[L.alpha_b] : params[L.rgb_b + c - 1];
+  }
+  dst[i] = v;
+}
+
+}  // namespace lush
+
 using namespace lush;
-bool lush_mlp_tc_supported(const MlpLayout& L) { (void)L; return false; }
-size_t lush_mlp_tc_stash_bytes(const MlpLayout&, int64_t, int) { return 0; }
-size_t lush_mlp_tc_workspace_bytes(const MlpLayout&, int64_t, int, int) { return 0; }
-int lush_mlp_tc_fwd(const MlpLayout&, const lush_mlp_desc*, const float*, const float*, int, const float*,
-                    float*, void*, void*, size_t, int64_t, int, cudaStream_t) { return LUSH_EUNSUPPORTED; }
+
+bool lush_mlp_tc_training_supported() { return false; }
+
+bool lush_mlp_tc_supported(const MlpLayout& L) {
+  return L.W == TW && L.out_mode == 0 && L.D >= 2 && L.D <= kMaxDepth && L.in_ch <= 64 && L.in_ch_v <= 32 &&
+         (L.skip < 0 || (L.skip >= 0 && L.skip < L.D - 1));
+}
+
+size_t lush_mlp_tc_stash_bytes(const MlpLayout& L, int64_t R, int S) {
+  (void)L; (void)R; (void)S;
+  return 0;  // training through the tcgen05 path lands with the dgrad/wgrad kernels
+}
+
+// workspace: [packed weight stream | gathered params]
+size_t lush_mlp_tc_workspace_bytes(const MlpLayout& L, int64_t R, int S, int training) {
+  (void)R; (void)S; (void)training;
+  FwdPlan P;
+  make_fwd_plan(L, P);
+  return (size_t)P.wstream_bytes + (size_t)P.nparam_floats * 4 + 256;
+}
+
+int lush_mlp_tc_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* params, const float* ray_batch,
+                    int ray_stride, const float* z, float* out, void* stash, void* workspace,
+                    size_t workspace_bytes, int64_t R, int S, cudaStream_t st) {
+  FwdPlan P;
+  make_fwd_plan(L, P);
+  const size_t need = lush_mlp_tc_workspace_bytes(L, R, S, 0);
+  if (!workspace || workspace_bytes < need) {
+    set_error("mlp_fwd(tc): workspace too small (%zu < %zu)", workspace_bytes, need);
+    return LUSH_EWORKSPACE;
+  }
+  LUSH_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)out & 15) == 0, "mlp_fwd(tc): unaligned buffers");
+  LUSH_REQUIRE(stash == nullptr, "mlp_fwd(tc): training stash not supported yet");
+  __half* wstream = reinterpret_cast<__half*>(workspace);
+  float* gparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((P.wstream_bytes + 255) / 256) * 256);
+  PackPlan K;
+  make_pack_plan(L, P, K);
+  pack_fwd_weights_kernel<<<dim3(64, K.njobs), 256, 0, st>>>(params, wstream, K);
+  LUSH_LAUNCH_CHECK("pack_fwd_weights");
+  gather_fwd_params_kernel<<<(P.nparam_floats + 255) / 256, 256, 0, st>>>(params, gparams, L, P);
+  LUSH_LAUNCH_CHECK("gather_fwd_params");
+  const int64_t M = R * S;
+  const int64_t ntiles = (M + TROWS - 1) / TROWS, nsuper = (ntiles + 1) / 2;
+  const size_t smem = fwd_smem_bytes(P);
+  LUSH_REQUIRE(smem <= 227 * 1024, "mlp_fwd(tc): shared memory budget exceeded (%zu)", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024), "mlp_fwd(tc): smem attr");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  int grid = (int)(nsuper < kNumSMs ? nsuper : kNumSMs);
+  mlp_tc_fwd_kernel<<<grid, FWD_THREADS, smem, st>>>(wstream, gparams, ray_batch, ray_stride, z, out,
+                                                    (uint8_t*)stash, M, S, desc->L_pts, desc->L_views, P);
+  LUSH_LAUNCH_CHECK("mlp_tc_fwd");
+  return 0;
+}
+
 int lush_mlp_tc_bwd(const MlpLayout&, const lush_mlp_desc*, const float*, const float*, int, const float*,
                     const float*, const void*, float*, float*, void*, size_t, int64_t, int, cudaStream_t) {
+  set_error("mlp_bwd(tc): not implemented yet");
   return LUSH_EUNSUPPORTED;
 }

@@ -192,8 +192,9 @@ class _Timed:
             MLP_EVENT_SINK.append((self.a, self.b))
 
 
-def mlp_impl_supported(desc: MlpDesc, impl: int) -> bool:
-    return bool(lib().lush_mlp_impl_supported(byref(desc), int(impl)))
+def mlp_impl_supported(desc: MlpDesc, impl: int, training: bool = False) -> bool:
+    caps = int(lib().lush_mlp_impl_supported(byref(desc), int(impl)))
+    return bool(caps & (2 if training else 1))
 
 
 class _MLP(torch.autograd.Function):

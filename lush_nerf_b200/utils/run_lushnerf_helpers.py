@@ -125,14 +125,17 @@ class _FlatParamMLP(nn.Module):
     def desc(self) -> MlpDesc:
         return self._desc
 
-    def impl(self) -> int:
+    def impl(self, training: bool = False) -> int:
+        """1 = tcgen05 fp16-operand kernels when they cover this topology (and this mode), else 0 = fp32 SIMT."""
         want = getattr(self, "mlp_impl", None)
         want = ops.default_mlp_impl() if want is None else want
-        return want if ops.mlp_impl_supported(self._desc, want) else 0
+        return want if ops.mlp_impl_supported(self._desc, want, training) else 0
 
     def render(self, ray_batch, z):
         """Fused encode+MLP on the samples x = o + d*z of each ray -> [R, S, C]."""
-        return ops.mlp_apply(ray_batch, z, self._desc, self.impl(), self.flat_params(), self._ordered_params())
+        ps = self._ordered_params()
+        training = torch.is_grad_enabled() and (ray_batch.requires_grad or any(p.requires_grad for p in ps))
+        return ops.mlp_apply(ray_batch, z, self._desc, self.impl(training), self.flat_params(), ps)
 
     def forward(self, x, force_naive=True, inference=False):
         """Reference call surface: x = [embedded pts | embedded views] (helpers:394).  The fused kernels

@@ -64,7 +64,9 @@ def test_param_counts_match_reference():
     L = _lib.lib()
     assert L.lush_mlp_param_count(_lib.MlpDesc(8, 256, 10, 4, 4, 0)) == 595844
     assert L.lush_mlp_param_count(_lib.MlpDesc(4, 128, 10, 4, 4, 1)) == 84548
-    assert L.lush_mlp_impl_supported(_lib.MlpDesc(8, 256, 10, 4, 4, 0), 0) == 1
+    assert L.lush_mlp_impl_supported(_lib.MlpDesc(8, 256, 10, 4, 4, 0), 0) == 3
+    assert L.lush_mlp_impl_supported(_lib.MlpDesc(8, 256, 10, 4, 4, 0), 1) & 1
+    assert L.lush_mlp_impl_supported(_lib.MlpDesc(4, 128, 10, 4, 4, 1), 1) == 0   # noise MLP: SIMT only
 
 
 def test_state_dict_names_shapes_and_aliases():

@@ -25,7 +25,8 @@ struct SampleFwd {
   float mask;    // eval near-plane mask (1 in training)
   float dist;
   float alpha;
-  float om;      // 1 - alpha
+  float om;      // 1 - alpha (what the reference multiplies into the transmittance)
+  float e;       // exp(-sigma*dist): d alpha / d(sigma*dist), more accurate than 1 - alpha when alpha ~ 1
 };
 
 __device__ __forceinline__ SampleFwd sample_fwd(const RayChunk& c, bool has_next, float dnorm,
@@ -37,11 +38,13 @@ __device__ __forceinline__ SampleFwd sample_fwd(const RayChunk& c, bool has_next
   if (thresh >= 0.f) f.mask = (c.zn > thresh) ? 1.f : 0.f;
   f.sigma = fmaxf(f.pre, 0.f) * f.mask;
   if (has_next) {
-    f.alpha = 1.f - expf(-(f.sigma * f.dist));
+    f.e = expf(-(f.sigma * f.dist));
+    f.alpha = 1.f - f.e;
   } else {  // last sample: alpha = 1 (reference :338), no density entry
     f.alpha = 1.f;
     f.sigma = 0.f;
     f.dist = 0.f;
+    f.e = 0.f;
   }
   f.om = 1.f - f.alpha;  // reference adds 1e-10 in fp32, which rounds away (-alpha + 1.0f)
   return f;
@@ -221,9 +224,9 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       go.w = 0.f;
       if (i + 1 < S) {
         float galpha = T * (G - Bi);
-        float gsig = galpha * f.dist * f.om + gden_in[k];
+        float gsig = galpha * f.dist * f.e + gden_in[k];
         go.w = (f.pre > 0.f) ? gsig * f.mask : 0.f;
-        gdn += galpha * f.sigma * f.om * (c.zn - c.z);
+        gdn += galpha * f.sigma * f.e * (c.zn - c.z);
       }
       reinterpret_cast<float4*>(g_raw)[r * S + i] = go;
     }

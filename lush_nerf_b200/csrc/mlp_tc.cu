@@ -216,7 +216,7 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
                   const float* __restrict__ ray_batch, int ray_stride, const float* __restrict__ z,
                   float* __restrict__ out, uint8_t* __restrict__ stash, int64_t M, int S, int L_pts,
                   int L_views, FwdPlan P) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], a_ready[2], d_ready[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -515,13 +515,11 @@ int lush_mlp_tc_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
   const int64_t M = R * S;
   const int64_t ntiles = (M + TROWS - 1) / TROWS, nsuper = (ntiles + 1) / 2;
   const size_t smem = fwd_smem_bytes(P);
-  LUSH_REQUIRE(smem <= 227 * 1024, "mlp_fwd(tc): shared memory budget exceeded (%zu)", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  LUSH_REQUIRE(smem + 256 <= 227 * 1024, "mlp_fwd(tc): shared memory budget exceeded (%zu)", smem);
+  {
     int rc = check_cuda(cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024), "mlp_fwd(tc): smem attr");
+                                             (int)smem), "mlp_fwd(tc): smem attr");
     if (rc) return rc;
-    attr_set = true;
   }
   int grid = (int)(nsuper < kNumSMs ? nsuper : kNumSMs);
   mlp_tc_fwd_kernel<<<grid, FWD_THREADS, smem, st>>>(wstream, gparams, ray_batch, ray_stride, z, out,

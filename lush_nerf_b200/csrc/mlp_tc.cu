@@ -13,90 +13,10 @@
 //               head (256->1) and rgb head (128->3) are register dot products in the epilogues; only
 //               [M,4] fp32 goes back to HBM (plus, in training, the fp16 activation stash for backward).
 // Activations: H tile [128 x 256] fp16 (64 KB) per tile, encodings [128 x 64] (16 KB) per tile.
-#include "mlp_common.cuh"
-#include "tc_common.cuh"
+#include "mlp_tc.cuh"
 
 namespace lush {
 using namespace tc;
-
-constexpr int TW = 256;            // network width this path is built for
-constexpr int TROWS = 128;         // rows per tile (= TMEM lanes)
-constexpr int KS = 32;             // K elements per weight slice
-constexpr int NSTAGE = 3;
-constexpr int STAGE_BYTES = TW * KS * 2;          // 16 KB
-constexpr int H_BYTES = TROWS * TW * 2;           // 64 KB
-constexpr int ENC_BYTES = TROWS * 64 * 2;         // 16 KB
-constexpr int ENCV_BYTES = TROWS * 32 * 2;        // 8 KB
-constexpr int HV_BYTES = TROWS * 128 * 2;         // 32 KB
-constexpr int MAX_STEPS = kMaxDepth + 2;
-constexpr int FWD_THREADS = 320;
-
-enum FwdEpi { EPI_TRUNK = 0, EPI_FEATURE = 1, EPI_VIEWS = 2 };
-
-struct FwdStep {
-  int N;           // output width (256 or 128)
-  int nslices;     // K slices of 32
-  int enc_slices;  // leading slices read the encoding buffer (ENC), the rest read H
-  int enc_first;   // 1: encoding segment comes first (layers 0 / skip+1); 0: H first, encoding last (views)
-  int epi;         // FwdEpi
-  int bias_off;    // float offset into the smem parameter block
-  int last_trunk;  // 1: also produce sigma = h . w_alpha + b
-  int stash_slot;  // index of the H blob this step's OUTPUT occupies in the stash record (training)
-};
-
-struct FwdPlan {
-  int nsteps;
-  int D;
-  FwdStep steps[MAX_STEPS];
-  // smem parameter block (floats): biases per step, then w_alpha[256], w_rgb[3][128], b_alpha, b_rgb[3]
-  int w_alpha_off, w_rgb_off, b_head_off, nparam_floats;
-  // stash record (bytes per tile)
-  int rec_bytes, rec_encp, rec_h0, rec_feat, rec_encv, rec_hv, rec_mask, rec_maskv;
-  int64_t wstream_bytes;
-};
-
-// ------------------------------------------------------------------------------------------------
-// host: plan + weight packing
-// ------------------------------------------------------------------------------------------------
-static void make_fwd_plan(const MlpLayout& L, FwdPlan& P) {
-  P.D = L.D;
-  int n = 0, boff = 0;
-  int64_t wbytes = 0;
-  for (int i = 0; i < L.D; ++i) {
-    FwdStep& s = P.steps[n++];
-    s.N = TW; s.epi = EPI_TRUNK; s.bias_off = boff; boff += TW;
-    s.last_trunk = (i == L.D - 1);
-    s.enc_first = 1;
-    if (i == 0) { s.nslices = 2; s.enc_slices = 2; }
-    else if (L.skip >= 0 && i == L.skip + 1) { s.nslices = 2 + TW / KS; s.enc_slices = 2; }
-    else { s.nslices = TW / KS; s.enc_slices = 0; }
-    s.stash_slot = i;
-    wbytes += (int64_t)s.nslices * s.N * KS * 2;
-  }
-  { FwdStep& s = P.steps[n++];
-    s.N = TW; s.epi = EPI_FEATURE; s.bias_off = boff; boff += TW; s.last_trunk = 0;
-    s.nslices = TW / KS; s.enc_slices = 0; s.enc_first = 1; s.stash_slot = L.D;
-    wbytes += (int64_t)s.nslices * s.N * KS * 2; }
-  { FwdStep& s = P.steps[n++];
-    s.N = 128; s.epi = EPI_VIEWS; s.bias_off = boff; boff += 128; s.last_trunk = 0;
-    s.nslices = TW / KS + 1; s.enc_slices = 1; s.enc_first = 0; s.stash_slot = -1;
-    wbytes += (int64_t)s.nslices * s.N * KS * 2; }
-  P.nsteps = n;
-  P.w_alpha_off = boff; boff += TW;
-  P.w_rgb_off = boff; boff += 3 * 128;
-  P.b_head_off = boff; boff += 4;
-  P.nparam_floats = boff;
-  P.wstream_bytes = wbytes;
-  int off = 0;
-  P.rec_encp = off; off += ENC_BYTES;
-  P.rec_h0 = off; off += L.D * H_BYTES;
-  P.rec_feat = off; off += H_BYTES;
-  P.rec_encv = off; off += ENCV_BYTES;
-  P.rec_hv = off; off += HV_BYTES;
-  P.rec_mask = off; off += L.D * TROWS * 32;   // 256 relu bits per row per trunk layer
-  P.rec_maskv = off; off += TROWS * 16;        // 128 bits per row for the views layer
-  P.rec_bytes = off;
-}
 
 // One thread per packed fp16 element of the forward weight stream.
 // Step s, slice j, element (n, kk): stream offset = step_base + j*N*KS*2 + (kk/8)*(N*16) + n*16 + (kk%8)*2
@@ -202,10 +122,6 @@ __device__ __forceinline__ void encode_row_to_smem(uint8_t* blob, int row, float
     q.w = pack_h2(vals[8 * g + 6], vals[8 * g + 7]);
     *reinterpret_cast<uint4*>(blob + g * (TROWS * 16) + row * 16) = q;
   }
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -472,7 +388,9 @@ __global__ void gather_fwd_params_kernel(const float* __restrict__ params, float
 
 using namespace lush;
 
-bool lush_mlp_tc_training_supported() { return false; }
+size_t lush_mlp_tc_bwd_workspace_bytes(const MlpLayout& L, int64_t R, int S);   // mlp_tc_bwd.cu
+
+bool lush_mlp_tc_training_supported() { return true; }
 
 bool lush_mlp_tc_supported(const MlpLayout& L) {
   return L.W == TW && L.out_mode == 0 && L.D >= 2 && L.D <= kMaxDepth && L.in_ch <= 64 && L.in_ch_v <= 32 &&
@@ -480,16 +398,27 @@ bool lush_mlp_tc_supported(const MlpLayout& L) {
 }
 
 size_t lush_mlp_tc_stash_bytes(const MlpLayout& L, int64_t R, int S) {
-  (void)L; (void)R; (void)S;
-  return 0;  // training through the tcgen05 path lands with the dgrad/wgrad kernels
-}
-
-// workspace: [packed weight stream | gathered params]
-size_t lush_mlp_tc_workspace_bytes(const MlpLayout& L, int64_t R, int S, int training) {
-  (void)R; (void)S; (void)training;
   FwdPlan P;
   make_fwd_plan(L, P);
-  return (size_t)P.wstream_bytes + (size_t)P.nparam_floats * 4 + 256;
+  const int64_t ntiles = (R * S + TROWS - 1) / TROWS;
+  return (size_t)ntiles * P.rec_bytes;
+}
+
+// forward workspace: [packed weight stream | gathered params]; backward: see mlp_tc_bwd.cu
+size_t lush_mlp_tc_workspace_bytes(const MlpLayout& L, int64_t R, int S, int training) {
+  if (training) return lush_mlp_tc_bwd_workspace_bytes(L, R, S);
+  FwdPlan P;
+  make_fwd_plan(L, P);
+  return (size_t)((P.wstream_bytes + 255) / 256) * 256 + (size_t)P.nparam_floats * 4 + 256;
+}
+
+// biases + head weights gathered into one float block (also used by the backward kernels)
+int lush_tc_gather_head_params(const MlpLayout& L, const float* params, float* dst, cudaStream_t st) {
+  FwdPlan P;
+  make_fwd_plan(L, P);
+  gather_fwd_params_kernel<<<(P.nparam_floats + 255) / 256, 256, 0, st>>>(params, dst, L, P);
+  LUSH_LAUNCH_CHECK("gather_fwd_params");
+  return 0;
 }
 
 int lush_mlp_tc_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* params, const float* ray_batch,
@@ -502,34 +431,26 @@ int lush_mlp_tc_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
     set_error("mlp_fwd(tc): workspace too small (%zu < %zu)", workspace_bytes, need);
     return LUSH_EWORKSPACE;
   }
-  LUSH_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)out & 15) == 0, "mlp_fwd(tc): unaligned buffers");
-  LUSH_REQUIRE(stash == nullptr, "mlp_fwd(tc): training stash not supported yet");
+  LUSH_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)stash & 15) == 0,
+               "mlp_fwd(tc): unaligned buffers");
   __half* wstream = reinterpret_cast<__half*>(workspace);
   float* gparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((P.wstream_bytes + 255) / 256) * 256);
   PackPlan K;
   make_pack_plan(L, P, K);
   pack_fwd_weights_kernel<<<dim3(64, K.njobs), 256, 0, st>>>(params, wstream, K);
   LUSH_LAUNCH_CHECK("pack_fwd_weights");
-  gather_fwd_params_kernel<<<(P.nparam_floats + 255) / 256, 256, 0, st>>>(params, gparams, L, P);
-  LUSH_LAUNCH_CHECK("gather_fwd_params");
+  int rc = lush_tc_gather_head_params(L, params, gparams, st);
+  if (rc) return rc;
   const int64_t M = R * S;
   const int64_t ntiles = (M + TROWS - 1) / TROWS, nsuper = (ntiles + 1) / 2;
   const size_t smem = fwd_smem_bytes(P);
   LUSH_REQUIRE(smem + 256 <= 227 * 1024, "mlp_fwd(tc): shared memory budget exceeded (%zu)", smem);
-  {
-    int rc = check_cuda(cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem), "mlp_fwd(tc): smem attr");
-    if (rc) return rc;
-  }
+  rc = check_cuda(cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                  "mlp_fwd(tc): smem attr");
+  if (rc) return rc;
   int grid = (int)(nsuper < kNumSMs ? nsuper : kNumSMs);
   mlp_tc_fwd_kernel<<<grid, FWD_THREADS, smem, st>>>(wstream, gparams, ray_batch, ray_stride, z, out,
                                                     (uint8_t*)stash, M, S, desc->L_pts, desc->L_views, P);
   LUSH_LAUNCH_CHECK("mlp_tc_fwd");
   return 0;
-}
-
-int lush_mlp_tc_bwd(const MlpLayout&, const lush_mlp_desc*, const float*, const float*, int, const float*,
-                    const float*, const void*, float*, float*, void*, size_t, int64_t, int, cudaStream_t) {
-  set_error("mlp_bwd(tc): not implemented yet");
-  return LUSH_EUNSUPPORTED;
 }

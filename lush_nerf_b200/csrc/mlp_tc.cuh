@@ -1,0 +1,93 @@
+// Shared plan / layout definitions of the tcgen05 MLP kernels (forward: mlp_tc.cu, backward: mlp_tc_bwd.cu).
+#pragma once
+#include "mlp_common.cuh"
+#include "tc_common.cuh"
+
+namespace lush {
+using namespace tc;
+
+constexpr int TW = 256;            // network width this path is built for
+constexpr int TROWS = 128;         // rows per tile (= TMEM lanes)
+constexpr int KS = 32;             // K elements per weight slice
+constexpr int NSTAGE = 3;
+constexpr int STAGE_BYTES = TW * KS * 2;          // 16 KB
+constexpr int H_BYTES = TROWS * TW * 2;           // 64 KB
+constexpr int ENC_BYTES = TROWS * 64 * 2;         // 16 KB
+constexpr int ENCV_BYTES = TROWS * 32 * 2;        // 8 KB
+constexpr int HV_BYTES = TROWS * 128 * 2;         // 32 KB
+constexpr int MAX_STEPS = kMaxDepth + 2;
+constexpr int FWD_THREADS = 320;
+
+enum FwdEpi { EPI_TRUNK = 0, EPI_FEATURE = 1, EPI_VIEWS = 2 };
+
+struct FwdStep {
+  int N;           // output width (256 or 128)
+  int nslices;     // K slices of 32
+  int enc_slices;  // leading slices read the encoding buffer (ENC), the rest read H
+  int enc_first;   // 1: encoding segment comes first (layers 0 / skip+1); 0: H first, encoding last (views)
+  int epi;         // FwdEpi
+  int bias_off;    // float offset into the smem parameter block
+  int last_trunk;  // 1: also produce sigma = h . w_alpha + b
+  int stash_slot;  // index of the H blob this step's OUTPUT occupies in the stash record (training)
+};
+
+struct FwdPlan {
+  int nsteps;
+  int D;
+  FwdStep steps[MAX_STEPS];
+  // smem parameter block (floats): biases per step, then w_alpha[256], w_rgb[3][128], b_alpha, b_rgb[3]
+  int w_alpha_off, w_rgb_off, b_head_off, nparam_floats;
+  // stash record (bytes per tile)
+  int rec_bytes, rec_encp, rec_h0, rec_feat, rec_encv, rec_hv, rec_mask, rec_maskv;
+  int64_t wstream_bytes;
+};
+
+// ------------------------------------------------------------------------------------------------
+// host: plan + weight packing
+// ------------------------------------------------------------------------------------------------
+static inline void make_fwd_plan(const MlpLayout& L, FwdPlan& P) {
+  P.D = L.D;
+  int n = 0, boff = 0;
+  int64_t wbytes = 0;
+  for (int i = 0; i < L.D; ++i) {
+    FwdStep& s = P.steps[n++];
+    s.N = TW; s.epi = EPI_TRUNK; s.bias_off = boff; boff += TW;
+    s.last_trunk = (i == L.D - 1);
+    s.enc_first = 1;
+    if (i == 0) { s.nslices = 2; s.enc_slices = 2; }
+    else if (L.skip >= 0 && i == L.skip + 1) { s.nslices = 2 + TW / KS; s.enc_slices = 2; }
+    else { s.nslices = TW / KS; s.enc_slices = 0; }
+    s.stash_slot = i;
+    wbytes += (int64_t)s.nslices * s.N * KS * 2;
+  }
+  { FwdStep& s = P.steps[n++];
+    s.N = TW; s.epi = EPI_FEATURE; s.bias_off = boff; boff += TW; s.last_trunk = 0;
+    s.nslices = TW / KS; s.enc_slices = 0; s.enc_first = 1; s.stash_slot = L.D;
+    wbytes += (int64_t)s.nslices * s.N * KS * 2; }
+  { FwdStep& s = P.steps[n++];
+    s.N = 128; s.epi = EPI_VIEWS; s.bias_off = boff; boff += 128; s.last_trunk = 0;
+    s.nslices = TW / KS + 1; s.enc_slices = 1; s.enc_first = 0; s.stash_slot = -1;
+    wbytes += (int64_t)s.nslices * s.N * KS * 2; }
+  P.nsteps = n;
+  P.w_alpha_off = boff; boff += TW;
+  P.w_rgb_off = boff; boff += 3 * 128;
+  P.b_head_off = boff; boff += 4;
+  P.nparam_floats = boff;
+  P.wstream_bytes = wbytes;
+  int off = 0;
+  P.rec_encp = off; off += ENC_BYTES;
+  P.rec_h0 = off; off += L.D * H_BYTES;
+  P.rec_feat = off; off += H_BYTES;
+  P.rec_encv = off; off += ENCV_BYTES;
+  P.rec_hv = off; off += HV_BYTES;
+  P.rec_mask = off; off += L.D * TROWS * 32;   // 256 relu bits per row per trunk layer
+  P.rec_maskv = off; off += TROWS * 16;        // 128 bits per row for the views layer
+  P.rec_bytes = off;
+}
+
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace lush

@@ -1,0 +1,812 @@
+// Backward of the fused scene MLP on tcgen05 (impl = 1 of lush_mlp_bwd), sm_100a.
+// Replaces the autograd graph of reference helpers:394-423 (mm x2 per Linear, threshold_backward, bias sums).
+//
+// Three stages over the fp16 activation stash written by the forward kernel (mlp_tc.cu):
+//  1. dgrad  (mlp_tc_dgrad_kernel): per 128-sample tile the chain dZ_L -> ... -> dZ_0 stays on chip exactly
+//     like the forward: weights (W^T, fp16, pre-packed) stream through a 3-stage bulk-copy ring, one thread
+//     issues tcgen05.mma for two tiles per slice, epilogue warpgroups apply the 1-bit ReLU masks and write
+//     the next A operand to shared memory; every dZ tile is also bulk-stored to HBM for stage 2.
+//     Gradients are carried in fp16 under a dynamic power-of-two loss scale (max|g_out| -> 32).
+//  2. wgrad  (mlp_tc_wgrad_kernel): dW_l = dZ_l^T . X_l with the reduction over samples; both operands are
+//     the SAME stash blobs read as MN-major UMMA operands; fp32 accumulators stay in TMEM across a chunk of
+//     tiles and are flushed once per chunk with fp32 atomics into the flat gradient buffer.  Bias gradients
+//     are column sums taken from the dZ stage in shared memory by the otherwise idle epilogue warps.
+//  3. small SIMT kernels: head gradients (sigma / rgb heads), per-ray reduction of d/d(o, d, viewdirs).
+#include "mlp_tc.cuh"
+
+namespace lush {
+
+constexpr int BWD_THREADS = 320;
+constexpr float kGradTarget = 32.f;   // scaled max |g_out|
+
+enum BwdEpi { BEPI_FEAT = 0, BEPI_TRUNK = 1, BEPI_ENC_SAVE = 2, BEPI_ENC_FINAL = 3 };
+
+struct BwdStep {
+  int N;           // output columns of this dgrad GEMM (256 or 64)
+  int nslices;     // reduction slices of 32 over the producing layer's output units
+  int epi;         // BwdEpi
+  int mask_layer;  // BEPI_TRUNK: trunk layer whose ReLU gates the result
+  int add_alpha;   // BEPI_TRUNK: add g_sigma * w_alpha (gradient into the last trunk activation)
+  int dz_off;      // byte offset inside the gstash record receiving the epilogue output (-1: none)
+};
+
+struct BwdPlan {
+  int nsteps;
+  BwdStep steps[MAX_STEPS + 2];
+  int has_skip_enc;     // an ENC_SAVE step exists (its result is added in ENC_FINAL)
+  int grec_bytes, grec_v, grec_f, grec_l0;   // gstash record: dZv | dZf | dZ_0 .. dZ_{D-1}
+  int64_t bstream_bytes;
+};
+
+struct BPackJob {
+  int64_t out_off, w_off;
+  int fan_in, col0, ncols_real, N, Kp;
+};
+struct BPackPlan {
+  int njobs;
+  BPackJob jobs[MAX_STEPS + 2];
+};
+
+static void make_bwd_plan(const MlpLayout& L, bool need_in, BwdPlan& B, BPackPlan& K) {
+  B.grec_v = 0;
+  B.grec_f = HV_BYTES;
+  B.grec_l0 = HV_BYTES + H_BYTES;
+  B.grec_bytes = B.grec_l0 + L.D * H_BYTES;
+  B.has_skip_enc = 0;
+  int n = 0;
+  int64_t off = 0;
+  auto add = [&](int N, int Kp, int epi, int mask_layer, int add_alpha, int dz_off, int64_t w_off, int fan_in,
+                 int col0, int ncols_real) {
+    BwdStep& s = B.steps[n];
+    s.N = N; s.nslices = Kp / KS; s.epi = epi; s.mask_layer = mask_layer; s.add_alpha = add_alpha; s.dz_off = dz_off;
+    BPackJob& J = K.jobs[n];
+    J.out_off = off; J.w_off = w_off; J.fan_in = fan_in; J.col0 = col0; J.ncols_real = ncols_real; J.N = N; J.Kp = Kp;
+    off += (int64_t)N * Kp * 2;
+    ++n;
+  };
+  // views layer: g_feat = dZv . Wv[:, 0:W]
+  add(TW, 128, BEPI_FEAT, -1, 0, B.grec_f, L.views_w, L.W + L.in_ch_v, 0, TW);
+  // feature layer: g_h_{D-1} = dZf . Wf (+ g_sigma w_alpha), ReLU mask of layer D-1
+  add(TW, TW, BEPI_TRUNK, L.D - 1, 1, B.grec_l0 + (L.D - 1) * H_BYTES, L.feat_w, L.W, 0, TW);
+  for (int l = L.D - 1; l >= 1; --l) {
+    const bool is_skip = (L.skip >= 0 && l == L.skip + 1);
+    if (is_skip && need_in) {
+      add(64, TW, BEPI_ENC_SAVE, -1, 0, -1, L.pts_w[l], L.pts_in[l], 0, L.in_ch);
+      B.has_skip_enc = 1;
+    }
+    add(TW, TW, BEPI_TRUNK, l - 1, 0, B.grec_l0 + (l - 1) * H_BYTES, L.pts_w[l], L.pts_in[l],
+        is_skip ? L.in_ch : 0, TW);
+  }
+  if (need_in) add(64, TW, BEPI_ENC_FINAL, -1, 0, -1, L.pts_w[0], L.pts_in[0], 0, L.in_ch);
+  B.nsteps = n;
+  K.njobs = n;
+  B.bstream_bytes = off;
+}
+
+// stream element (kin, n) of a step = W[n, col0 + kin]  (B operand [N x Kp], K-major over n)
+__global__ void pack_bwd_weights_kernel(const float* __restrict__ params, __half* __restrict__ stream,
+                                        BPackPlan plan) {
+  const BPackJob& J = plan.jobs[blockIdx.y];
+  const int64_t total = (int64_t)J.N * J.Kp;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int per_slice = J.N * KS;
+    int j = (int)(e / per_slice);
+    int rem = (int)(e - (int64_t)j * per_slice);
+    int g = rem / (J.N * 8);
+    int rem2 = rem - g * J.N * 8;
+    int kin = rem2 / 8, n8 = rem2 % 8;
+    int nn = j * KS + g * 8 + n8;   // producing layer's output unit (reduction index)
+    float v = (kin < J.ncols_real) ? params[J.w_off + (int64_t)nn * J.fan_in + J.col0 + kin] : 0.f;
+    stream[J.out_off / 2 + e] = __float2half_rn(v);
+  }
+}
+
+// max |g_out| as float bits (non-negative floats order like unsigned ints)
+__global__ void absmax_kernel(const float* __restrict__ g, int64_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = fabsf(g[i]);
+    if (v == v && v < INFINITY) m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+__device__ __forceinline__ float grad_scale_from(const unsigned* buf) {
+  float m = __uint_as_float(*buf);
+  if (!(m > 0.f)) return 1.f;
+  float e = floorf(log2f(kGradTarget / m));
+  e = fminf(fmaxf(e, -60.f), 60.f);
+  return exp2f(e);
+}
+
+struct DgSmem {
+  static constexpr int G0 = 0;
+  static constexpr int ENC0 = 2 * H_BYTES;
+  static constexpr int STAGE0 = ENC0 + 2 * ENC_BYTES;
+  static constexpr int PARAMS = STAGE0 + NSTAGE * STAGE_BYTES;   // w_alpha[256], w_rgb[384]
+  static constexpr int TOTAL = PARAMS + (TW + 384) * 4;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 1: fused dgrad chain
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+mlp_tc_dgrad_kernel(const __half* __restrict__ bstream, const float* __restrict__ head_params,
+                    const float* __restrict__ g_out, const unsigned* __restrict__ scale_buf,
+                    const uint8_t* __restrict__ fstash, uint8_t* __restrict__ gstash, float* __restrict__ g_x,
+                    const float* __restrict__ ray_batch, int ray_stride, const float* __restrict__ z, int64_t M,
+                    int S, int L_pts, FwdPlan P, BwdPlan B) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], a_ready[2], d_ready[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (M + TROWS - 1) / TROWS;
+  const int64_t nsuper = (ntiles + 1) / 2;
+  float* sparams = reinterpret_cast<float*>(smem + DgSmem::PARAMS);
+  for (int i = tid; i < TW + 384; i += BWD_THREADS) sparams[i] = head_params[P.w_alpha_off + i];
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&a_ready[t], 128); mbar_init(&d_ready[t], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(bstream);
+        for (int s = 0; s < B.nsteps; ++s) {
+          const uint32_t bytes = (uint32_t)B.steps[s].N * KS * 2;
+          for (int j = 0; j < B.steps[s].nslices; ++j) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            bulk_g2s(smem + DgSmem::STAGE0 + stage * STAGE_BYTES, src, bytes, &full_bar[stage]);
+            src += bytes;
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t a_phase[2] = {0, 0};
+      const uint32_t sbase = smem_u32(smem);
+      for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
+        const int nt = (2 * st + 1 < ntiles) ? 2 : 1;
+        for (int s = 0; s < B.nsteps; ++s) {
+          const BwdStep& S_ = B.steps[s];
+          const uint32_t idesc = make_idesc_f16(TROWS, S_.N, 0, 0);
+          const uint32_t b_lbo = (uint32_t)S_.N * 16u;
+          for (int j = 0; j < S_.nslices; ++j) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            for (int t = 0; t < nt; ++t) {
+              if (j == 0) { mbar_wait(&a_ready[t], a_phase[t]); a_phase[t] ^= 1; tc_fence_after(); }
+              const uint32_t abuf = sbase + DgSmem::G0 + t * H_BYTES;
+#pragma unroll
+              for (int kk = 0; kk < KS / 16; ++kk) {
+                const uint64_t ad = make_smem_desc(abuf + (uint32_t)((j * KS + kk * 16) / 8) * (TROWS * 16u), TROWS * 16u, 128u);
+                const uint64_t bd = make_smem_desc(sbase + DgSmem::STAGE0 + stage * STAGE_BYTES + kk * 2u * b_lbo, b_lbo, 128u);
+                umma_f16(tmem_base + t * 256, ad, bd, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&d_ready[0]);
+          if (nt > 1) umma_commit(&d_ready[1]);
+        }
+      }
+    }
+  } else {
+    const int t = (warp - 2) >> 2;
+    const int row = 32 * (warp & 3) + lane;
+    const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
+    uint8_t* Gb = smem + DgSmem::G0 + t * H_BYTES;
+    uint8_t* Eb = smem + DgSmem::ENC0 + t * ENC_BYTES;
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const int bar_id = 1 + t;
+    const float scale = grad_scale_from(scale_buf);
+    const float inv_scale = 1.f / scale;
+    const float* wa = sparams;
+    const float* wr = sparams + TW;
+    uint32_t d_phase = 0;
+    for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
+      const int64_t tile = 2 * st + t;
+      if (tile >= ntiles) continue;
+      const int64_t m = tile * TROWS + row;
+      const bool valid = m < M;
+      const uint8_t* frec = fstash + tile * (int64_t)P.rec_bytes;
+      uint8_t* grec = gstash + tile * (int64_t)B.grec_bytes;
+      // ---- prologue: dZ of the views layer from g_out (rgb head backward + ReLU mask)
+      float4 g = valid ? reinterpret_cast<const float4*>(g_out)[m] : make_float4(0.f, 0.f, 0.f, 0.f);
+      g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
+      const float g_sigma = g.w;
+      {
+        const uint4 mv = *reinterpret_cast<const uint4*>(frec + P.rec_maskv + row * 16);
+        const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+        if (leader) bulk_wait_read_all();
+        named_bar_sync(bar_id, 128);
+#pragma unroll 4
+        for (int gq = 0; gq < 16; ++gq) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = gq * 8 + i;
+            float x = g.x * wr[j] + g.y * wr[128 + j] + g.z * wr[256 + j];
+            v[i] = ((mw[j >> 5] >> (j & 31)) & 1u) ? x : 0.f;
+          }
+          uint4 q;
+          q.x = pack_h2(v[0], v[1]); q.y = pack_h2(v[2], v[3]); q.z = pack_h2(v[4], v[5]); q.w = pack_h2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(Gb + gq * (TROWS * 16) + row * 16) = q;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&a_ready[t]);
+      named_bar_sync(bar_id, 128);
+      if (leader) { bulk_s2g(grec + B.grec_v, Gb, HV_BYTES); bulk_commit(); }
+
+      for (int s = 0; s < B.nsteps; ++s) {
+        const BwdStep& S_ = B.steps[s];
+        const bool last = (s == B.nsteps - 1);
+        uint32_t mw[8];
+        if (S_.epi == BEPI_TRUNK) {   // prefetch the 256 ReLU bits of this row before waiting on the MMA
+          const uint4* mp = reinterpret_cast<const uint4*>(frec + P.rec_mask + (S_.mask_layer * TROWS + row) * 32);
+          const uint4 m0 = mp[0], m1 = mp[1];
+          mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w; mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+        }
+        mbar_wait(&d_ready[t], d_phase); d_phase ^= 1;
+        tc_fence_after();
+        if (S_.epi == BEPI_FEAT || S_.epi == BEPI_TRUNK) {
+          if (leader) bulk_wait_read_all();   // the previous dZ blob is still being stored from Gb
+          named_bar_sync(bar_id, 128);
+#pragma unroll 1
+          for (int cc = 0; cc < TW; cc += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + tlane + t * 256 + cc, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r[j]);
+              if (S_.epi == BEPI_TRUNK) {
+                if (S_.add_alpha) x = fmaf(g_sigma, wa[cc + j], x);
+                x = ((mw[cc >> 5] >> j) & 1u) ? x : 0.f;
+              }
+              v[j] = x;
+            }
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              uint4 q;
+              q.x = pack_h2(v[8 * gq + 0], v[8 * gq + 1]); q.y = pack_h2(v[8 * gq + 2], v[8 * gq + 3]);
+              q.z = pack_h2(v[8 * gq + 4], v[8 * gq + 5]); q.w = pack_h2(v[8 * gq + 6], v[8 * gq + 7]);
+              *reinterpret_cast<uint4*>(Gb + ((cc >> 3) + gq) * (TROWS * 16) + row * 16) = q;
+            }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          if (!last) mbar_arrive(&a_ready[t]);
+          named_bar_sync(bar_id, 128);
+          if (leader) { bulk_s2g(grec + S_.dz_off, Gb, H_BYTES); bulk_commit(); }
+        } else if (S_.epi == BEPI_ENC_SAVE) {
+#pragma unroll 1
+          for (int cc = 0; cc < 64; cc += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + tlane + t * 256 + cc, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              uint4 q;
+              q.x = pack_h2(__uint_as_float(r[8 * gq + 0]), __uint_as_float(r[8 * gq + 1]));
+              q.y = pack_h2(__uint_as_float(r[8 * gq + 2]), __uint_as_float(r[8 * gq + 3]));
+              q.z = pack_h2(__uint_as_float(r[8 * gq + 4]), __uint_as_float(r[8 * gq + 5]));
+              q.w = pack_h2(__uint_as_float(r[8 * gq + 6]), __uint_as_float(r[8 * gq + 7]));
+              *reinterpret_cast<uint4*>(Eb + ((cc >> 3) + gq) * (TROWS * 16) + row * 16) = q;
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&a_ready[t]);   // the A operand (Gb) is unchanged; the accumulator columns are free again
+        } else {  // BEPI_ENC_FINAL: d/d(gamma(x)) -> d/dx through the encoder
+          float ge[64];
+#pragma unroll
+          for (int cc = 0; cc < 64; cc += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + tlane + t * 256 + cc, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ge[cc + j] = __uint_as_float(r[j]);
+          }
+          if (B.has_skip_enc) {
+#pragma unroll
+            for (int gq = 0; gq < 8; ++gq) {
+              float v[8];
+              unpack8(*reinterpret_cast<const uint4*>(Eb + gq * (TROWS * 16) + row * 16), v);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ge[gq * 8 + i] += v[i];
+            }
+          }
+          if (valid && g_x != nullptr) {
+            const int64_t rr = m / S;
+            const float* rb = ray_batch + rr * ray_stride;
+            const float zz = z[m];
+            float x[3];
+            x[0] = __fadd_rn(rb[0], __fmul_rn(rb[3], zz));
+            x[1] = __fadd_rn(rb[1], __fmul_rn(rb[4], zz));
+            x[2] = __fadd_rn(rb[2], __fmul_rn(rb[5], zz));
+            float gx[3] = {ge[0], ge[1], ge[2]};
+            float f = 1.f;
+#pragma unroll
+            for (int l = 0; l < 10; ++l) {
+              if (l < L_pts) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  float sn, cs;
+                  sincosf(x[c] * f, &sn, &cs);
+                  gx[c] += f * (cs * ge[3 + 6 * l + c] - sn * ge[3 + 6 * l + 3 + c]);
+                }
+              }
+              f *= 2.f;
+            }
+            g_x[m * 3 + 0] = gx[0] * inv_scale;
+            g_x[m * 3 + 1] = gx[1] * inv_scale;
+            g_x[m * 3 + 2] = gx[2] * inv_scale;
+          }
+          tc_fence_before();
+          if (!last) mbar_arrive(&a_ready[t]);
+        }
+      }
+    }
+    if (leader) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 2: wgrad
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 192;           // producer warp, MMA warp, 4 epilogue warps
+constexpr int WG_STAGE_BYTES = 65536;     // 64 samples: dZ [64 x <=256] (32 KB) | X [64 x <=256] (32 KB)
+constexpr int WG_NSTAGE = 3;
+constexpr int MAX_WJOBS = 2 * kMaxDepth + 8;
+
+struct WJob {
+  int dz_off, nout;          // dZ blob inside the gstash record, its width (256 | 128)
+  int x_off, kin, kin_real;  // X blob inside the forward stash record, padded / real width
+  int64_t w_off;             // dW destination: g_params[w_off + n*fan_in + col0 + k]
+  int fan_in, col0;
+  int64_t b_off;             // bias-gradient destination (nout floats) or -1
+};
+struct WPlan {
+  int njobs, nchunks, tiles_per_chunk;
+  WJob jobs[MAX_WJOBS];
+};
+
+static void make_wgrad_plan(const MlpLayout& L, const FwdPlan& P, const BwdPlan& B, int64_t ntiles, WPlan& Wp) {
+  int n = 0;
+  auto add = [&](int dz_off, int nout, int x_off, int kin, int kin_real, int64_t w_off, int fan_in, int col0,
+                 int64_t b_off) {
+    WJob& J = Wp.jobs[n++];
+    J.dz_off = dz_off; J.nout = nout; J.x_off = x_off; J.kin = kin; J.kin_real = kin_real; J.w_off = w_off;
+    J.fan_in = fan_in; J.col0 = col0; J.b_off = b_off;
+  };
+  // heaviest jobs first (units are dealt round-robin to the persistent CTAs)
+  for (int l = L.D - 1; l >= 1; --l) {
+    const bool is_skip = (L.skip >= 0 && l == L.skip + 1);
+    add(B.grec_l0 + l * H_BYTES, TW, P.rec_h0 + (l - 1) * H_BYTES, TW, TW, L.pts_w[l], L.pts_in[l],
+        is_skip ? L.in_ch : 0, L.pts_b[l]);
+  }
+  add(B.grec_f, TW, P.rec_h0 + (L.D - 1) * H_BYTES, TW, TW, L.feat_w, L.W, 0, L.feat_b);
+  add(B.grec_v, 128, P.rec_feat, TW, TW, L.views_w, L.W + L.in_ch_v, 0, L.views_b);
+  add(B.grec_l0, TW, P.rec_encp, 64, L.in_ch, L.pts_w[0], L.pts_in[0], 0, L.pts_b[0]);
+  if (L.skip >= 0 && L.skip + 1 < L.D)
+    add(B.grec_l0 + (L.skip + 1) * H_BYTES, TW, P.rec_encp, 64, L.in_ch, L.pts_w[L.skip + 1], L.pts_in[L.skip + 1], 0, -1);
+  add(B.grec_v, 128, P.rec_encv, 32, L.in_ch_v, L.views_w, L.W + L.in_ch_v, L.W, -1);
+  Wp.njobs = n;
+  // ~3 waves of units over the SMs
+  int64_t want_chunks = (3 * (int64_t)kNumSMs + n - 1) / n;
+  if (want_chunks > ntiles) want_chunks = ntiles;
+  if (want_chunks < 1) want_chunks = 1;
+  Wp.tiles_per_chunk = (int)((ntiles + want_chunks - 1) / want_chunks);
+  Wp.nchunks = (int)((ntiles + Wp.tiles_per_chunk - 1) / Wp.tiles_per_chunk);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restrict__ gstash,
+                    const unsigned* __restrict__ scale_buf, float* __restrict__ g_params, int64_t ntiles,
+                    int frec_bytes, int grec_bytes, WPlan Wp) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full_bar[WG_NSTAGE], empty_bar[WG_NSTAGE], acc_ready, acc_free;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < WG_NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1 + 4); }
+    mbar_init(&acc_ready, 1);
+    mbar_init(&acc_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int nunits = Wp.njobs * Wp.nchunks;
+
+  if (warp == 0) {
+    // ---- producer: 1 KB bulk copies (64 rows of one 8-column group) issued by all 32 lanes
+    int stage = 0; uint32_t phase = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const WJob& J = Wp.jobs[u / Wp.nchunks];
+      const int64_t t0 = (int64_t)(u % Wp.nchunks) * Wp.tiles_per_chunk;
+      const int64_t t1 = (t0 + Wp.tiles_per_chunk < ntiles) ? t0 + Wp.tiles_per_chunk : ntiles;
+      const int ga = J.nout / 8, gb = J.kin / 8;
+      for (int64_t tile = t0; tile < t1; ++tile) {
+        const uint8_t* asrc = gstash + tile * (int64_t)grec_bytes + J.dz_off;
+        const uint8_t* bsrc = fstash + tile * (int64_t)frec_bytes + J.x_off;
+        for (int half = 0; half < 2; ++half) {
+          if (lane == 0) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(ga + gb) * 1024u);
+          }
+          __syncwarp();
+          uint8_t* sa = smem + stage * WG_STAGE_BYTES;
+          uint8_t* sb = sa + 32768;
+          for (int gi = lane; gi < ga; gi += 32) bulk_g2s(sa + gi * 1024, asrc + gi * 2048 + half * 1024, 1024, &full_bar[stage]);
+          for (int gi = lane; gi < gb; gi += 32) bulk_g2s(sb + gi * 1024, bsrc + gi * 2048 + half * 1024, 1024, &full_bar[stage]);
+          if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, free_phase = 0;
+      const uint32_t sbase = smem_u32(smem);
+      bool first_unit = true;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const WJob& J = Wp.jobs[u / Wp.nchunks];
+        const int64_t t0 = (int64_t)(u % Wp.nchunks) * Wp.tiles_per_chunk;
+        const int64_t t1 = (t0 + Wp.tiles_per_chunk < ntiles) ? t0 + Wp.tiles_per_chunk : ntiles;
+        const uint32_t idesc = make_idesc_f16(128, J.kin, 1, 1);
+        if (!first_unit) { mbar_wait(&acc_free, free_phase); free_phase ^= 1; tc_fence_after(); }
+        first_unit = false;
+        bool first = true;
+        for (int64_t it = 0; it < 2 * (t1 - t0); ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * WG_STAGE_BYTES, sb = sa + 32768;
+          for (int h = 0; h < J.nout / 128; ++h) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = make_smem_desc(sa + h * 16 * 1024 + kk * 256, 128u, 1024u);
+              const uint64_t bd = make_smem_desc(sb + kk * 256, 128u, 1024u);
+              umma_f16(tmem_base + h * 256, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+            }
+          }
+          first = false;
+          umma_commit(&empty_bar[stage]);
+          if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_ready);
+      }
+    }
+  } else {
+    // ---- epilogue warps: bias column sums from the dZ stage while the MMAs run, then the accumulator flush
+    const int et = tid - 64;                 // 0..127
+    const int row = 32 * (warp & 3) + lane;  // TMEM lane = output unit within the 128-unit half
+    const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
+    const int q = et >> 3, r8 = et & 7;
+    const float inv_scale = 1.f / grad_scale_from(scale_buf);
+    int stage = 0; uint32_t phase = 0, ready_phase = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const WJob& J = Wp.jobs[u / Wp.nchunks];
+      const int64_t t0 = (int64_t)(u % Wp.nchunks) * Wp.tiles_per_chunk;
+      const int64_t t1 = (t0 + Wp.tiles_per_chunk < ntiles) ? t0 + Wp.tiles_per_chunk : ntiles;
+      const int ngrp = J.nout / 8;           // 32 or 16 column groups
+      float bs[2][8];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bs[a][i] = 0.f;
+      for (int64_t it = 0; it < 2 * (t1 - t0); ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        if (J.b_off >= 0) {
+          const uint8_t* sa = smem + stage * WG_STAGE_BYTES;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const int gi = q + 16 * a;
+            if (gi < ngrp) {
+#pragma unroll
+              for (int rr = 0; rr < 8; ++rr) {
+                float v[8];
+                unpack8(*reinterpret_cast<const uint4*>(sa + gi * 1024 + (r8 + 8 * rr) * 16), v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bs[a][i] += v[i];
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      if (J.b_off >= 0) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int gi = q + 16 * a;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float v = bs[a][i];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            if (r8 == 0 && gi < ngrp) atomicAdd(g_params + J.b_off + gi * 8 + i, v * inv_scale);
+          }
+        }
+      }
+      mbar_wait(&acc_ready, ready_phase); ready_phase ^= 1;
+      tc_fence_after();
+      for (int h = 0; h < J.nout / 128; ++h) {
+        float* dst = g_params + J.w_off + (int64_t)(h * 128 + row) * J.fan_in + J.col0;
+#pragma unroll 1
+        for (int cc = 0; cc < J.kin; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + tlane + h * 256 + cc, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cc + j < J.kin_real) atomicAdd(dst + cc + j, __uint_as_float(r[j]) * inv_scale);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 3a: head gradients (sigma head 256->1 and rgb head 128->3), fp32 g_out x fp16 stash
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_grads_kernel(const uint8_t* __restrict__ fstash, const float* __restrict__ g_out, float* __restrict__ g_params,
+                  int64_t M, int64_t ntiles, int frec_bytes, int h_last_off, int hv_off, int64_t alpha_w,
+                  int64_t alpha_b, int64_t rgb_w, int64_t rgb_b, int tiles_per_block) {
+  __shared__ float4 sg[TROWS];
+  const int tid = threadIdx.x;
+  float acc_a = 0.f, acc_r[3] = {0.f, 0.f, 0.f}, acc_b = 0.f;
+  const int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
+  const int64_t t1 = (t0 + tiles_per_block < ntiles) ? t0 + tiles_per_block : ntiles;
+  for (int64_t tile = t0; tile < t1; ++tile) {
+    __syncthreads();
+    if (tid < TROWS) {
+      const int64_t m = tile * TROWS + tid;
+      sg[tid] = (m < M) ? reinterpret_cast<const float4*>(g_out)[m] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const uint8_t* rec = fstash + tile * (int64_t)frec_bytes;
+    {   // sigma head: column tid of the last trunk activation
+      const __half* hp = reinterpret_cast<const __half*>(rec + h_last_off + (tid >> 3) * (TROWS * 16) + (tid & 7) * 2);
+      for (int s = 0; s < TROWS; ++s) acc_a = fmaf(sg[s].w, __half2float(hp[s * 8]), acc_a);
+    }
+    if (tid < 128) {   // rgb head: column tid of the views hidden layer
+      const __half* hp = reinterpret_cast<const __half*>(rec + hv_off + (tid >> 3) * (TROWS * 16) + (tid & 7) * 2);
+      for (int s = 0; s < TROWS; ++s) {
+        const float h = __half2float(hp[s * 8]);
+        acc_r[0] = fmaf(sg[s].x, h, acc_r[0]);
+        acc_r[1] = fmaf(sg[s].y, h, acc_r[1]);
+        acc_r[2] = fmaf(sg[s].z, h, acc_r[2]);
+      }
+    } else if (tid < 132) {   // head biases
+      const int c = tid - 128;
+      for (int s = 0; s < TROWS; ++s) {
+        const float4 v = sg[s];
+        acc_b += (c == 0) ? v.x : (c == 1) ? v.y : (c == 2) ? v.z : v.w;
+      }
+    }
+  }
+  atomicAdd(g_params + alpha_w + tid, acc_a);
+  if (tid < 128) {
+    atomicAdd(g_params + rgb_w + tid, acc_r[0]);
+    atomicAdd(g_params + rgb_w + 128 + tid, acc_r[1]);
+    atomicAdd(g_params + rgb_w + 256 + tid, acc_r[2]);
+  } else if (tid < 132) {
+    const int c = tid - 128;
+    atomicAdd(g_params + (c < 3 ? rgb_b + c : alpha_b), acc_b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 3b: per-ray reduction  d/d(o), d/d(d) from per-sample d/dx;  d/d(viewdirs) from sum_s dZv
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+ray_grad_reduce_kernel(const float* __restrict__ g_x, const float* __restrict__ z,
+                       const uint8_t* __restrict__ gstash, int grec_bytes, int grec_v,
+                       const float* __restrict__ params, int64_t views_w, int fan_in_v, int in_ch_v, int L_views,
+                       const float* __restrict__ ray_batch, int ray_stride, const unsigned* __restrict__ scale_buf,
+                       float* __restrict__ g_rb, int64_t R, int S) {
+  __shared__ float s_sum[4][128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * 4 + w;
+  if (r >= R) return;
+  const float inv_scale = 1.f / grad_scale_from(scale_buf);
+  float go[3] = {0, 0, 0}, gd[3] = {0, 0, 0};
+  for (int s = lane; s < S; s += 32) {
+    const int64_t m = r * S + s;
+    const float zz = z[m];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = g_x[m * 3 + c];
+      go[c] += v;
+      gd[c] += v * zz;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { go[c] = warp_sum(go[c]); gd[c] = warp_sum(gd[c]); }
+  // sum of the views-layer dZ over the samples of this ray
+  for (int gq = 0; gq < 16; ++gq) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = lane; s < S; s += 32) {
+      const int64_t m = r * S + s;
+      const int64_t tile = m / TROWS;
+      const int row = (int)(m - tile * TROWS);
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(gstash + tile * (int64_t)grec_bytes + grec_v + gq * (TROWS * 16) + row * 16), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = warp_sum(a[i]);
+      if (lane == i) s_sum[w][gq * 8 + i] = t;
+    }
+  }
+  __syncwarp();
+  float ge = 0.f;   // lane q < in_ch_v: d/d gamma(v)[q]
+  if (lane < in_ch_v) {
+    for (int j = 0; j < 128; ++j) ge = fmaf(s_sum[w][j], params[views_w + (int64_t)j * fan_in_v + TW + lane], ge);
+    ge *= inv_scale;
+  }
+  const float* rb = ray_batch + r * ray_stride;
+  float gv = 0.f;
+  {
+    const int c = lane < 3 ? lane : 0;
+    const float x = rb[8 + c];
+    gv = __shfl_sync(0xffffffffu, ge, c);
+    float f = 1.f;
+    for (int l = 0; l < L_views; ++l) {
+      float sn, cs;
+      sincosf(x * f, &sn, &cs);
+      const float gs = __shfl_sync(0xffffffffu, ge, 3 + 6 * l + c);
+      const float gc = __shfl_sync(0xffffffffu, ge, 3 + 6 * l + 3 + c);
+      gv += f * (cs * gs - sn * gc);
+      f *= 2.f;
+    }
+  }
+  float* o = g_rb + r * 11;
+  if (lane == 0) {
+    o[0] = go[0]; o[1] = go[1]; o[2] = go[2]; o[3] = gd[0]; o[4] = gd[1]; o[5] = gd[2]; o[6] = 0.f; o[7] = 0.f;
+  }
+  if (lane < 3) o[8 + lane] = gv;
+}
+
+}  // namespace lush
+
+using namespace lush;
+
+int lush_tc_gather_head_params(const MlpLayout& L, const float* params, float* dst, cudaStream_t st);  // mlp_tc.cu
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct BwdWorkspace {
+  size_t bstream, head, scale, gx, gstash, total;
+};
+static BwdWorkspace bwd_ws_layout(const MlpLayout& L, int64_t M, bool need_in) {
+  FwdPlan P; make_fwd_plan(L, P);
+  BwdPlan B; BPackPlan K; make_bwd_plan(L, need_in, B, K);
+  const int64_t ntiles = (M + TROWS - 1) / TROWS;
+  BwdWorkspace w;
+  size_t off = 0;
+  w.bstream = off; off = align256(off + (size_t)B.bstream_bytes);
+  w.head = off; off = align256(off + (size_t)P.nparam_floats * 4);
+  w.scale = off; off = align256(off + 256);
+  w.gx = off; off = align256(off + (size_t)M * 3 * 4);
+  w.gstash = off; off = align256(off + (size_t)ntiles * B.grec_bytes);
+  w.total = off;
+  return w;
+}
+
+size_t lush_mlp_tc_bwd_workspace_bytes(const MlpLayout& L, int64_t R, int S) {
+  return bwd_ws_layout(L, R * S, true).total;
+}
+
+int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* params, const float* ray_batch,
+                    int ray_stride, const float* z, const float* g_out, const void* stash, float* g_params,
+                    float* g_ray_batch, void* workspace, size_t workspace_bytes, int64_t R, int S, cudaStream_t st) {
+  const int64_t M = R * S;
+  const bool need_in = g_ray_batch != nullptr;
+  FwdPlan P; make_fwd_plan(L, P);
+  BwdPlan B; BPackPlan K; make_bwd_plan(L, need_in, B, K);
+  const BwdWorkspace w = bwd_ws_layout(L, M, true);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("mlp_bwd(tc): workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    return LUSH_EWORKSPACE;
+  }
+  LUSH_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)stash & 15) == 0 && ((uintptr_t)g_out & 15) == 0,
+               "mlp_bwd(tc): unaligned buffers");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __half* bstream = reinterpret_cast<__half*>(ws + w.bstream);
+  float* head = reinterpret_cast<float*>(ws + w.head);
+  unsigned* scale_buf = reinterpret_cast<unsigned*>(ws + w.scale);
+  float* gx = reinterpret_cast<float*>(ws + w.gx);
+  uint8_t* gstash = ws + w.gstash;
+  const uint8_t* fstash = reinterpret_cast<const uint8_t*>(stash);
+  const int64_t ntiles = (M + TROWS - 1) / TROWS, nsuper = (ntiles + 1) / 2;
+
+  int rc = check_cuda(cudaMemsetAsync(scale_buf, 0, 256, st), "mlp_bwd(tc): memset");
+  if (rc) return rc;
+  absmax_kernel<<<(unsigned)(M * 4 / 1024 < 1 ? 1 : (M * 4 / 1024 > 1184 ? 1184 : M * 4 / 1024)), 256, 0, st>>>(g_out, M * 4, scale_buf);
+  LUSH_LAUNCH_CHECK("absmax");
+  pack_bwd_weights_kernel<<<dim3(64, K.njobs), 256, 0, st>>>(params, bstream, K);
+  LUSH_LAUNCH_CHECK("pack_bwd_weights");
+  rc = lush_tc_gather_head_params(L, params, head, st);
+  if (rc) return rc;
+  {
+    const size_t smem = DgSmem::TOTAL;
+    rc = check_cuda(cudaFuncSetAttribute(mlp_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "mlp_bwd(tc): dgrad smem attr");
+    if (rc) return rc;
+    int grid = (int)(nsuper < kNumSMs ? nsuper : kNumSMs);
+    mlp_tc_dgrad_kernel<<<grid, BWD_THREADS, smem, st>>>(bstream, head, g_out, scale_buf, fstash, gstash,
+                                                        need_in ? gx : nullptr, ray_batch, ray_stride, z, M, S,
+                                                        desc->L_pts, P, B);
+    LUSH_LAUNCH_CHECK("mlp_tc_dgrad");
+  }
+  {
+    WPlan Wp; make_wgrad_plan(L, P, B, ntiles, Wp);
+    const size_t smem = (size_t)WG_NSTAGE * WG_STAGE_BYTES;
+    rc = check_cuda(cudaFuncSetAttribute(mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "mlp_bwd(tc): wgrad smem attr");
+    if (rc) return rc;
+    const int nunits = Wp.njobs * Wp.nchunks;
+    int grid = nunits < kNumSMs ? nunits : kNumSMs;
+    mlp_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(fstash, gstash, scale_buf, g_params, ntiles, P.rec_bytes,
+                                                       B.grec_bytes, Wp);
+    LUSH_LAUNCH_CHECK("mlp_tc_wgrad");
+  }
+  {
+    const int tpb = (int)((ntiles + 2 * kNumSMs - 1) / (2 * kNumSMs));
+    const int nblk = (int)((ntiles + tpb - 1) / tpb);
+    head_grads_kernel<<<nblk, 256, 0, st>>>(fstash, g_out, g_params, M, ntiles, P.rec_bytes,
+                                            P.rec_h0 + (L.D - 1) * H_BYTES, P.rec_hv, L.alpha_w, L.alpha_b, L.rgb_w,
+                                            L.rgb_b, tpb);
+    LUSH_LAUNCH_CHECK("head_grads");
+  }
+  if (need_in) {
+    ray_grad_reduce_kernel<<<(unsigned)((R + 3) / 4), 128, 0, st>>>(gx, z, gstash, B.grec_bytes, B.grec_v, params,
+                                                                   L.views_w, L.W + L.in_ch_v, L.in_ch_v,
+                                                                   desc->L_views, ray_batch, ray_stride, scale_buf,
+                                                                   g_ray_batch, R, S);
+    LUSH_LAUNCH_CHECK("ray_grad_reduce");
+  }
+  return 0;
+}

@@ -269,7 +269,12 @@ struct Launcher {
     g.a1 = Seg{G, ldg, 0, 1}; g.a2 = Seg{nullptr, 0, 0, 1};
     g.B = X; g.ldb = ldx; g.b_row_div = x_row_div; g.C = dW; g.ldc = lddw;
     g.Mout = N; g.Nout = K; g.Kred = M; g.atomic = 1;
-    int64_t chunk = 4096;
+    // enough (output tile, sample chunk) blocks to fill the 148 SMs twice, also when M is small
+    const int64_t bxy = ceil_div(N, BM) * ceil_div(K, BN);
+    int64_t chunk = ceil_div(M, ceil_div(2 * kNumSMs, bxy));
+    chunk = ((chunk + 15) / 16) * 16;
+    if (chunk < 64) chunk = 64;
+    if (chunk > 4096) chunk = 4096;
     g.kchunk = chunk;
     dim3 grid((unsigned)ceil_div(N, BM), (unsigned)ceil_div(K, BN), (unsigned)ceil_div(M, chunk));
     gemm_kernel<false, false><<<grid, 256, 0, st>>>(g);
@@ -278,7 +283,9 @@ struct Launcher {
   }
   void bias_grad(const float* G, int ldg, int64_t M, int N, float* db) {
     if (rc) return;
-    int rows = 2048;
+    int rows = (int)ceil_div(M, 2 * kNumSMs);
+    if (rows < 16) rows = 16;
+    if (rows > 2048) rows = 2048;
     dim3 grid((unsigned)ceil_div(M, rows), (unsigned)ceil_div(N, 128));
     bias_grad_kernel<<<grid, 128, 0, st>>>(G, ldg, M, N, db, rows);
     count_launch();

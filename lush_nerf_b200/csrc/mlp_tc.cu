@@ -19,10 +19,12 @@ namespace lush {
 using namespace tc;
 
 // One thread per packed fp16 element of the forward weight stream.
-// Step s, slice j, element (n, kk): stream offset = step_base + j*N*KS*2 + (kk/8)*(N*16) + n*16 + (kk%8)*2
+// Step s = nslices regular slices [N x 32] followed by one bias slice [N x 16] (column 0 = bias).
+// element (n, kk) of slice j: offset = step_base + j*N*KS*2 + (kk/8)*(N*16) + n*16 + (kk%8)*2
 struct PackJob {
   int64_t out_off;   // byte offset of the step in the stream
   int64_t w_off;     // float offset of the [N, fan_in] weight in the flat params
+  int64_t b_off;     // float offset of the bias [N]
   int N, fan_in, nslices;
   int enc_slices, enc_first, enc_real, enc_col0, main_col0;  // column mapping (see pack kernel)
 };
@@ -34,27 +36,36 @@ struct PackPlan {
 __global__ void pack_fwd_weights_kernel(const float* __restrict__ params, __half* __restrict__ stream,
                                         PackPlan plan) {
   const PackJob& J = plan.jobs[blockIdx.y];
-  const int64_t total = (int64_t)J.nslices * J.N * KS;
+  const int64_t nreg = (int64_t)J.nslices * J.N * KS;
+  const int64_t total = nreg + (int64_t)J.N * 16;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
        e += (int64_t)gridDim.x * blockDim.x) {
-    int j = (int)(e / (J.N * KS));
-    int rem = (int)(e - (int64_t)j * J.N * KS);
-    int kk8 = rem / (J.N * 8);          // which 8-column group inside the slice
-    int rem2 = rem - kk8 * J.N * 8;
-    int n = rem2 / 8, k8 = rem2 % 8;
-    int k = j * KS + kk8 * 8 + k8;      // K index within the step (padded, concatenated segments)
-    // map to the nn.Linear column
-    int col = -1;
-    const int enc_k = J.enc_slices * KS;
-    const int main_k = (J.nslices - J.enc_slices) * KS;
-    if (J.enc_first) {
-      if (k < enc_k) { if (k < J.enc_real) col = J.enc_col0 + k; }
-      else col = J.main_col0 + (k - enc_k);
+    float v = 0.f;
+    if (e < nreg) {
+      int j = (int)(e / (J.N * KS));
+      int rem = (int)(e - (int64_t)j * J.N * KS);
+      int kk8 = rem / (J.N * 8);          // which 8-column group inside the slice
+      int rem2 = rem - kk8 * J.N * 8;
+      int n = rem2 / 8, k8 = rem2 % 8;
+      int k = j * KS + kk8 * 8 + k8;      // K index within the step (padded, concatenated segments)
+      int col = -1;                       // nn.Linear column
+      const int enc_k = J.enc_slices * KS;
+      const int main_k = (J.nslices - J.enc_slices) * KS;
+      if (J.enc_first) {
+        if (k < enc_k) { if (k < J.enc_real) col = J.enc_col0 + k; }
+        else col = J.main_col0 + (k - enc_k);
+      } else {
+        if (k < main_k) col = J.main_col0 + k;
+        else if (k - main_k < J.enc_real) col = J.enc_col0 + (k - main_k);
+      }
+      if (col >= 0) v = params[J.w_off + (int64_t)n * J.fan_in + col];
     } else {
-      if (k < main_k) col = J.main_col0 + k;
-      else if (k - main_k < J.enc_real) col = J.enc_col0 + (k - main_k);
+      int rem = (int)(e - nreg);          // bias slice: [N x 16], only column 0 is non-zero
+      int g = rem / (J.N * 8);
+      int rem2 = rem - g * J.N * 8;
+      int n = rem2 / 8, k8 = rem2 % 8;
+      if (g == 0 && k8 == 0) v = params[J.b_off + n];
     }
-    float v = (col >= 0) ? params[J.w_off + (int64_t)n * J.fan_in + col] : 0.f;
     stream[J.out_off / 2 + e] = __float2half_rn(v);
   }
 }
@@ -68,16 +79,16 @@ static void make_pack_plan(const MlpLayout& L, const FwdPlan& P, PackPlan& K) {
     J.out_off = off;
     J.N = st.N; J.nslices = st.nslices; J.enc_slices = st.enc_slices; J.enc_first = st.enc_first;
     if (s < L.D) {
-      J.w_off = L.pts_w[s]; J.fan_in = L.pts_in[s];
+      J.w_off = L.pts_w[s]; J.b_off = L.pts_b[s]; J.fan_in = L.pts_in[s];
       J.enc_real = L.in_ch; J.enc_col0 = 0;
       J.main_col0 = (st.enc_slices && s > 0) ? L.in_ch : 0;   // skip layer: [input | hidden] (helpers:401)
     } else if (s == L.D) {
-      J.w_off = L.feat_w; J.fan_in = L.W; J.enc_real = 0; J.enc_col0 = 0; J.main_col0 = 0;
+      J.w_off = L.feat_w; J.b_off = L.feat_b; J.fan_in = L.W; J.enc_real = 0; J.enc_col0 = 0; J.main_col0 = 0;
     } else {
-      J.w_off = L.views_w; J.fan_in = L.W + L.in_ch_v;       // [feature | views] (helpers:409)
+      J.w_off = L.views_w; J.b_off = L.views_b; J.fan_in = L.W + L.in_ch_v;   // [feature | views] (helpers:409)
       J.enc_real = L.in_ch_v; J.enc_col0 = L.W; J.main_col0 = 0;
     }
-    off += (int64_t)st.nslices * st.N * KS * 2;
+    off += (int64_t)st.nslices * st.N * KS * 2 + (int64_t)st.N * 16 * 2;
   }
 }
 
@@ -89,7 +100,8 @@ struct FwdSmem {
   static constexpr int H0 = 0;
   static constexpr int ENC0 = 2 * H_BYTES;
   static constexpr int STAGE0 = ENC0 + 2 * ENC_BYTES;
-  static constexpr int PARAMS = STAGE0 + NSTAGE * STAGE_BYTES;
+  static constexpr int ONES = STAGE0 + NSTAGE * STAGE_BYTES;   // [128 x 16] fp16, column 0 = 1 (bias operand)
+  static constexpr int PARAMS = ONES + TROWS * 16 * 2;
 };
 
 // gamma(x) for one coordinate triple into the tile-canonical [128 x 64] (or [128 x 32]) fp16 blob, row `row`.
@@ -124,9 +136,38 @@ __device__ __forceinline__ void encode_row_to_smem(uint8_t* blob, int row, float
   }
 }
 
+// 32 accumulator columns -> fp16 (optionally through ReLU) -> 4 x 16-byte stores in the operand layout
+template <bool RELU>
+__device__ __forceinline__ void store_chunk(uint8_t* Hb, int cc, int row, const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 q;
+    if (RELU) {
+      q.x = pack_h2_relu(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
+      q.y = pack_h2_relu(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+      q.z = pack_h2_relu(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+      q.w = pack_h2_relu(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+    } else {
+      q.x = pack_h2(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
+      q.y = pack_h2(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+      q.z = pack_h2(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+      q.w = pack_h2(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+    }
+    *reinterpret_cast<uint4*>(Hb + ((cc >> 3) + g) * (TROWS * 16) + row * 16) = q;
+  }
+}
+// sign bits of 32 accumulators, MSB-first: bit (31-j) = 1 iff column j is negative (ReLU inactive)
+__device__ __forceinline__ uint32_t sign_bits(const uint32_t (&r)[32]) {
+  uint32_t mb = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) mb = __funnelshift_l(r[j], mb, 1);
+  return mb;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------
+template <bool TRAIN>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ params_smem_src,
                   const float* __restrict__ ray_batch, int ray_stride, const float* __restrict__ z,
@@ -142,12 +183,16 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
   float* sparams = reinterpret_cast<float*>(smem + FwdSmem::PARAMS);
 
   for (int i = tid; i < P.nparam_floats; i += FWD_THREADS) sparams[i] = params_smem_src[i];
+  for (int i = tid; i < TROWS * 16 * 2 / 16; i += FWD_THREADS)   // ones operand: row r -> [1,0,...,0 | 0 x 8]
+    *reinterpret_cast<uint4*>(smem + FwdSmem::ONES + i * 16) = (i < TROWS) ? make_uint4(0x3C00u, 0u, 0u, 0u)
+                                                                            : make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int t = 0; t < 2; ++t) { mbar_init(&a_ready[t], 4 * 32); mbar_init(&d_ready[t], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -160,8 +205,9 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
       for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(wstream);
         for (int s = 0; s < P.nsteps; ++s) {
-          const uint32_t bytes = (uint32_t)P.steps[s].N * KS * 2;
-          for (int j = 0; j < P.steps[s].nslices; ++j) {
+          const int ns = P.steps[s].nslices;
+          for (int j = 0; j <= ns; ++j) {   // j == ns: the bias slice (K = 16)
+            const uint32_t bytes = (uint32_t)P.steps[s].N * (j < ns ? KS : 16) * 2;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], bytes);
             bulk_g2s(smem + FwdSmem::STAGE0 + stage * STAGE_BYTES, src, bytes, &full_bar[stage]);
@@ -183,21 +229,29 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
           const FwdStep& S_ = P.steps[s];
           const uint32_t idesc = make_idesc_f16(TROWS, S_.N, 0, 0);
           const uint32_t b_lbo = (uint32_t)S_.N * 16u;
-          for (int j = 0; j < S_.nslices; ++j) {
+          for (int j = 0; j <= S_.nslices; ++j) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            // which activation buffer / column does this slice read?
-            bool from_enc; int kcol;
-            if (S_.enc_first) { from_enc = j < S_.enc_slices; kcol = from_enc ? j * KS : (j - S_.enc_slices) * KS; }
-            else { const int mainsl = S_.nslices - S_.enc_slices; from_enc = j >= mainsl; kcol = from_enc ? (j - mainsl) * KS : j * KS; }
-            for (int t = 0; t < nt; ++t) {
-              if (j == 0) { mbar_wait(&a_ready[t], a_phase[t]); a_phase[t] ^= 1; tc_fence_after(); }
-              const uint32_t abuf = sbase + (from_enc ? FwdSmem::ENC0 + t * ENC_BYTES : FwdSmem::H0 + t * H_BYTES);
+            const uint32_t bbuf = sbase + FwdSmem::STAGE0 + stage * STAGE_BYTES;
+            if (j == S_.nslices) {
+              // bias: ones[128 x 16] . biasrow[N x 16]^T accumulated on top of the layer product
+              const uint64_t ad = make_smem_desc(sbase + FwdSmem::ONES, TROWS * 16u, 128u);
+              const uint64_t bd = make_smem_desc(bbuf, b_lbo, 128u);
+              for (int t = 0; t < nt; ++t) umma_f16(tmem_base + t * 256, ad, bd, idesc, 1u);
+            } else {
+              // which activation buffer / column does this slice read?
+              bool from_enc; int kcol;
+              if (S_.enc_first) { from_enc = j < S_.enc_slices; kcol = from_enc ? j * KS : (j - S_.enc_slices) * KS; }
+              else { const int mainsl = S_.nslices - S_.enc_slices; from_enc = j >= mainsl; kcol = from_enc ? (j - mainsl) * KS : j * KS; }
+              for (int t = 0; t < nt; ++t) {
+                if (j == 0) { mbar_wait(&a_ready[t], a_phase[t]); a_phase[t] ^= 1; tc_fence_after(); }
+                const uint32_t abuf = sbase + (from_enc ? FwdSmem::ENC0 + t * ENC_BYTES : FwdSmem::H0 + t * H_BYTES);
 #pragma unroll
-              for (int kk = 0; kk < KS / 16; ++kk) {
-                const uint64_t ad = make_smem_desc(abuf + (uint32_t)((kcol + kk * 16) / 8) * (TROWS * 16u), TROWS * 16u, 128u);
-                const uint64_t bd = make_smem_desc(sbase + FwdSmem::STAGE0 + stage * STAGE_BYTES + kk * 2u * b_lbo, b_lbo, 128u);
-                umma_f16(tmem_base + t * 256, ad, bd, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                for (int kk = 0; kk < KS / 16; ++kk) {
+                  const uint64_t ad = make_smem_desc(abuf + (uint32_t)((kcol + kk * 16) / 8) * (TROWS * 16u), TROWS * 16u, 128u);
+                  const uint64_t bd = make_smem_desc(bbuf + kk * 2u * b_lbo, b_lbo, 128u);
+                  umma_f16(tmem_base + t * 256, ad, bd, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                }
               }
             }
             umma_commit(&empty_bar[stage]);
@@ -217,13 +271,16 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
     uint8_t* Eb = smem + FwdSmem::ENC0 + t * ENC_BYTES;
     const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
     const int bar_id = 1 + t;
+    const float4* wa4 = reinterpret_cast<const float4*>(sparams + P.w_alpha_off);
+    const float* wr = sparams + P.w_rgb_off;
     uint32_t d_phase = 0;
     for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
       const int64_t tile = 2 * st + t;
       if (tile >= ntiles) continue;
       const int64_t m = tile * TROWS + row;
       const bool valid = m < M;
-      uint8_t* rec = stash ? stash + tile * (int64_t)P.rec_bytes : nullptr;
+      uint8_t* rec = TRAIN ? stash + tile * (int64_t)P.rec_bytes : nullptr;
+      const uint32_t tacc = tmem_base + tlane + t * 256;
       // ---- prologue: sample point + encodings
       float vx = 0.f, vy = 0.f, vz = 0.f;
       {
@@ -237,55 +294,51 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
           x2 = __fadd_rn(rb[2], __fmul_rn(rb[5], zz));
           vx = rb[8]; vy = rb[9]; vz = rb[10];
         }
-        if (rec && leader) bulk_wait_read_all();       // previous tile's stash stores still read H/ENC
-        if (rec) named_bar_sync(bar_id, 128);
+        if (TRAIN) {                                   // previous tile's stash stores still read H/ENC
+          if (leader) bulk_wait_read_all();
+          named_bar_sync(bar_id, 128);
+        }
         encode_row_to_smem<64>(Eb, row, x0, x1, x2, L_pts);
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&a_ready[t]);
-      if (rec) {
+      if (TRAIN) {
         named_bar_sync(bar_id, 128);
         if (leader) { bulk_s2g(rec + P.rec_encp, Eb, ENC_BYTES); bulk_commit(); }
       }
       float alpha = 0.f;
       for (int s = 0; s < P.nsteps; ++s) {
         const FwdStep& S_ = P.steps[s];
-        const float* bias = sparams + S_.bias_off;
         mbar_wait(&d_ready[t], d_phase); d_phase ^= 1;
         tc_fence_after();
-        if (rec) {                                     // the H blob of the previous step is being stored
+        uint32_t ra[32], rb2[32];
+        tmem_ld32(tacc, ra);                           // overlaps with the stash bookkeeping below
+        if (TRAIN) {                                   // the H blob of the previous step is being stored
           if (leader) bulk_wait_read_all();
           named_bar_sync(bar_id, 128);
         }
         if (S_.epi == EPI_VIEWS) {
           float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-          const float* wr = sparams + P.w_rgb_off;
           uint32_t mbits[4];
-#pragma unroll 1
-          for (int cc = 0; cc < 128; cc += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + tlane + t * 256 + cc, r);
-            tmem_ld_wait();
-            uint32_t mb = 0;
-            float hv[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float v = fmaxf(__uint_as_float(r[j]) + bias[cc + j], 0.f);
-              hv[j] = v;
-              mb |= (v > 0.f ? 1u : 0u) << j;
-              c0 = fmaf(v, wr[cc + j], c0);
-              c1 = fmaf(v, wr[128 + cc + j], c1);
-              c2 = fmaf(v, wr[256 + cc + j], c2);
-            }
-            mbits[cc >> 5] = mb;
-            if (rec) {
+          for (int cc = 0; cc < 128; cc += 64) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 q;
-                q.x = pack_h2(hv[8 * g + 0], hv[8 * g + 1]); q.y = pack_h2(hv[8 * g + 2], hv[8 * g + 3]);
-                q.z = pack_h2(hv[8 * g + 4], hv[8 * g + 5]); q.w = pack_h2(hv[8 * g + 6], hv[8 * g + 7]);
-                *reinterpret_cast<uint4*>(Hb + ((cc >> 3) + g) * (TROWS * 16) + row * 16) = q;
+            for (int hb = 0; hb < 2; ++hb) {
+              uint32_t (&r)[32] = hb ? rb2 : ra;
+              const int c = cc + 32 * hb;
+              tmem_ld_wait();
+              if (c + 32 < 128) tmem_ld32(tacc + c + 32, hb ? ra : rb2);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = fmaxf(__uint_as_float(r[j]), 0.f);
+                c0 = fmaf(v, wr[c + j], c0);
+                c1 = fmaf(v, wr[128 + c + j], c1);
+                c2 = fmaf(v, wr[256 + c + j], c2);
+              }
+              if (TRAIN) {
+                mbits[c >> 5] = sign_bits(r);
+                store_chunk<true>(Hb, c, row, r);
               }
             }
           }
@@ -294,7 +347,7 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
             float4 o = make_float4(c0 + bh[1], c1 + bh[2], c2 + bh[3], alpha + bh[0]);
             reinterpret_cast<float4*>(out)[m] = o;
           }
-          if (rec) {
+          if (TRAIN) {
             *reinterpret_cast<uint4*>(rec + P.rec_maskv + row * 16) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
             fence_proxy_async();
             named_bar_sync(bar_id, 128);
@@ -303,38 +356,32 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
           tc_fence_before();   // orders our TMEM reads before the next tile's a_ready arrive
         } else {
           uint32_t mbits[8];
-#pragma unroll 1
-          for (int cc = 0; cc < TW; cc += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + tlane + t * 256 + cc, r);
-            tmem_ld_wait();
-            float v[32];
-            uint32_t mb = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(r[j]) + bias[cc + j];
-              if (S_.epi == EPI_TRUNK) x = fmaxf(x, 0.f);
-              v[j] = x;
-              mb |= (x > 0.f ? 1u : 0u) << j;
-            }
-            mbits[cc >> 5] = mb;
-            if (S_.last_trunk) {
-              const float* wa = sparams + P.w_alpha_off;
+          for (int cc = 0; cc < TW; cc += 64) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) alpha = fmaf(v[j], wa[cc + j], alpha);
-            }
+            for (int hb = 0; hb < 2; ++hb) {
+              uint32_t (&r)[32] = hb ? rb2 : ra;
+              const int c = cc + 32 * hb;
+              tmem_ld_wait();
+              if (c + 32 < TW) tmem_ld32(tacc + c + 32, hb ? ra : rb2);
+              if (TRAIN && S_.epi == EPI_TRUNK) mbits[c >> 5] = sign_bits(r);
+              if (S_.last_trunk) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 q;
-              q.x = pack_h2(v[8 * g + 0], v[8 * g + 1]); q.y = pack_h2(v[8 * g + 2], v[8 * g + 3]);
-              q.z = pack_h2(v[8 * g + 4], v[8 * g + 5]); q.w = pack_h2(v[8 * g + 6], v[8 * g + 7]);
-              *reinterpret_cast<uint4*>(Hb + ((cc >> 3) + g) * (TROWS * 16) + row * 16) = q;
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 w4 = wa4[(c >> 2) + j4];
+                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), w4.x, alpha);
+                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f), w4.y, alpha);
+                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), w4.z, alpha);
+                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f), w4.w, alpha);
+                }
+              }
+              if (S_.epi == EPI_TRUNK) store_chunk<true>(Hb, c, row, r);
+              else store_chunk<false>(Hb, c, row, r);
             }
           }
           if (S_.epi == EPI_FEATURE)   // the encoding buffer is dead after the trunk: reuse it for gamma(viewdirs)
             encode_row_to_smem<32>(Eb, row, vx, vy, vz, L_views);
-          if (S_.last_trunk) alpha = valid ? alpha : 0.f;
-          if (rec && S_.epi == EPI_TRUNK) {
+          if (TRAIN && S_.epi == EPI_TRUNK) {
             uint4* mp = reinterpret_cast<uint4*>(rec + P.rec_mask + (s * TROWS + row) * 32);
             mp[0] = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
             mp[1] = make_uint4(mbits[4], mbits[5], mbits[6], mbits[7]);
@@ -342,7 +389,7 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(&a_ready[t]);
-          if (rec) {
+          if (TRAIN) {
             named_bar_sync(bar_id, 128);
             if (leader) {
               bulk_s2g(rec + P.rec_h0 + S_.stash_slot * H_BYTES, Hb, H_BYTES);
@@ -353,7 +400,7 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
         }
       }
     }
-    if (stash && leader) bulk_wait_all();
+    if (TRAIN && leader) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -362,20 +409,13 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
 
 static size_t fwd_smem_bytes(const FwdPlan& P) { return (size_t)FwdSmem::PARAMS + (size_t)P.nparam_floats * 4; }
 
-// gathers biases + head weights into one contiguous float block (the kernel copies it to smem)
+// head weights gathered into one contiguous float block: w_alpha[256] | w_rgb[3][128] | b_alpha, b_rgb[3]
 __global__ void gather_fwd_params_kernel(const float* __restrict__ params, float* __restrict__ dst, MlpLayout L,
                                          FwdPlan P) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.nparam_floats) return;
   float v;
-  if (i < P.w_alpha_off) {
-    int s = 0;
-    while (s + 1 < P.nsteps && i >= P.steps[s + 1].bias_off) ++s;
-    int c = i - P.steps[s].bias_off;
-    if (s < L.D) v = params[L.pts_b[s] + c];
-    else if (s == L.D) v = params[L.feat_b + c];
-    else v = params[L.views_b + c];
-  } else if (i < P.w_rgb_off) v = params[L.alpha_w + (i - P.w_alpha_off)];
+  if (i < P.w_rgb_off) v = params[L.alpha_w + (i - P.w_alpha_off)];
   else if (i < P.b_head_off) v = params[L.rgb_w + (i - P.w_rgb_off)];
   else {
     int c = i - P.b_head_off;
@@ -445,12 +485,20 @@ int lush_mlp_tc_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
   const int64_t ntiles = (M + TROWS - 1) / TROWS, nsuper = (ntiles + 1) / 2;
   const size_t smem = fwd_smem_bytes(P);
   LUSH_REQUIRE(smem + 256 <= 227 * 1024, "mlp_fwd(tc): shared memory budget exceeded (%zu)", smem);
-  rc = check_cuda(cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                  "mlp_fwd(tc): smem attr");
-  if (rc) return rc;
   int grid = (int)(nsuper < kNumSMs ? nsuper : kNumSMs);
-  mlp_tc_fwd_kernel<<<grid, FWD_THREADS, smem, st>>>(wstream, gparams, ray_batch, ray_stride, z, out,
-                                                    (uint8_t*)stash, M, S, desc->L_pts, desc->L_views, P);
+  if (stash != nullptr) {
+    rc = check_cuda(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem), "mlp_fwd(tc): smem attr");
+    if (rc) return rc;
+    mlp_tc_fwd_kernel<true><<<grid, FWD_THREADS, smem, st>>>(wstream, gparams, ray_batch, ray_stride, z, out,
+                                                            (uint8_t*)stash, M, S, desc->L_pts, desc->L_views, P);
+  } else {
+    rc = check_cuda(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem), "mlp_fwd(tc): smem attr");
+    if (rc) return rc;
+    mlp_tc_fwd_kernel<false><<<grid, FWD_THREADS, smem, st>>>(wstream, gparams, ray_batch, ray_stride, z, out,
+                                                             nullptr, M, S, desc->L_pts, desc->L_views, P);
+  }
   LUSH_LAUNCH_CHECK("mlp_tc_fwd");
   return 0;
 }

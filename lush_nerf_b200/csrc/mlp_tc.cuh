@@ -26,7 +26,7 @@ struct FwdStep {
   int enc_slices;  // leading slices read the encoding buffer (ENC), the rest read H
   int enc_first;   // 1: encoding segment comes first (layers 0 / skip+1); 0: H first, encoding last (views)
   int epi;         // FwdEpi
-  int bias_off;    // float offset into the smem parameter block
+  int bias_src;    // 0: pts_linears[i].bias, 1: feature_linear.bias, 2: views_linears.0.bias (folded into the MMA)
   int last_trunk;  // 1: also produce sigma = h . w_alpha + b
   int stash_slot;  // index of the H blob this step's OUTPUT occupies in the stash record (training)
 };
@@ -35,7 +35,8 @@ struct FwdPlan {
   int nsteps;
   int D;
   FwdStep steps[MAX_STEPS];
-  // smem parameter block (floats): biases per step, then w_alpha[256], w_rgb[3][128], b_alpha, b_rgb[3]
+  // smem parameter block (floats): w_alpha[256], w_rgb[3][128], b_alpha, b_rgb[3]
+  // (layer biases ride in the weight stream as one extra K=16 slice per step against a ones column)
   int w_alpha_off, w_rgb_off, b_head_off, nparam_floats;
   // stash record (bytes per tile)
   int rec_bytes, rec_encp, rec_h0, rec_feat, rec_encv, rec_hv, rec_mask, rec_maskv;
@@ -48,26 +49,27 @@ struct FwdPlan {
 static inline void make_fwd_plan(const MlpLayout& L, FwdPlan& P) {
   P.D = L.D;
   int n = 0, boff = 0;
+  auto step_bytes = [](const FwdStep& s) { return (int64_t)s.nslices * s.N * KS * 2 + (int64_t)s.N * 16 * 2; };
   int64_t wbytes = 0;
   for (int i = 0; i < L.D; ++i) {
     FwdStep& s = P.steps[n++];
-    s.N = TW; s.epi = EPI_TRUNK; s.bias_off = boff; boff += TW;
+    s.N = TW; s.epi = EPI_TRUNK; s.bias_src = 0;
     s.last_trunk = (i == L.D - 1);
     s.enc_first = 1;
     if (i == 0) { s.nslices = 2; s.enc_slices = 2; }
     else if (L.skip >= 0 && i == L.skip + 1) { s.nslices = 2 + TW / KS; s.enc_slices = 2; }
     else { s.nslices = TW / KS; s.enc_slices = 0; }
     s.stash_slot = i;
-    wbytes += (int64_t)s.nslices * s.N * KS * 2;
+    wbytes += step_bytes(s);
   }
   { FwdStep& s = P.steps[n++];
-    s.N = TW; s.epi = EPI_FEATURE; s.bias_off = boff; boff += TW; s.last_trunk = 0;
+    s.N = TW; s.epi = EPI_FEATURE; s.bias_src = 1; s.last_trunk = 0;
     s.nslices = TW / KS; s.enc_slices = 0; s.enc_first = 1; s.stash_slot = L.D;
-    wbytes += (int64_t)s.nslices * s.N * KS * 2; }
+    wbytes += step_bytes(s); }
   { FwdStep& s = P.steps[n++];
-    s.N = 128; s.epi = EPI_VIEWS; s.bias_off = boff; boff += 128; s.last_trunk = 0;
+    s.N = 128; s.epi = EPI_VIEWS; s.bias_src = 2; s.last_trunk = 0;
     s.nslices = TW / KS + 1; s.enc_slices = 1; s.enc_first = 0; s.stash_slot = -1;
-    wbytes += (int64_t)s.nslices * s.N * KS * 2; }
+    wbytes += step_bytes(s); }
   P.nsteps = n;
   P.w_alpha_off = boff; boff += TW;
   P.w_rgb_off = boff; boff += 3 * 128;

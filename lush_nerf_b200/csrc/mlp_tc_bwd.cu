@@ -250,7 +250,7 @@ mlp_tc_dgrad_kernel(const __half* __restrict__ bstream, const float* __restrict_
           for (int i = 0; i < 8; ++i) {
             const int j = gq * 8 + i;
             float x = g.x * wr[j] + g.y * wr[128 + j] + g.z * wr[256 + j];
-            v[i] = ((mw[j >> 5] >> (j & 31)) & 1u) ? x : 0.f;
+            v[i] = ((mw[j >> 5] >> (31 - (j & 31))) & 1u) ? 0.f : x;   // stash bit = 1: unit was inactive
           }
           uint4 q;
           q.x = pack_h2(v[0], v[1]); q.y = pack_h2(v[2], v[3]); q.z = pack_h2(v[4], v[5]); q.w = pack_h2(v[6], v[7]);
@@ -288,7 +288,7 @@ mlp_tc_dgrad_kernel(const __half* __restrict__ bstream, const float* __restrict_
               float x = __uint_as_float(r[j]);
               if (S_.epi == BEPI_TRUNK) {
                 if (S_.add_alpha) x = fmaf(g_sigma, wa[cc + j], x);
-                x = ((mw[cc >> 5] >> j) & 1u) ? x : 0.f;
+                x = ((mw[cc >> 5] >> (31 - j)) & 1u) ? 0.f : x;
               }
               v[j] = x;
             }
@@ -587,51 +587,78 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
 // ------------------------------------------------------------------------------------------------
 // stage 3a: head gradients (sigma head 256->1 and rgb head 128->3), fp32 g_out x fp16 stash
 // ------------------------------------------------------------------------------------------------
+// lane = sample row (coalesced 16-byte loads along a blob column group), warp w owns column groups
+// w, w+8, ... ; per-thread partial sums over all tiles of the block, one shuffle reduction at the end.
 __global__ void __launch_bounds__(256)
 head_grads_kernel(const uint8_t* __restrict__ fstash, const float* __restrict__ g_out, float* __restrict__ g_params,
                   int64_t M, int64_t ntiles, int frec_bytes, int h_last_off, int hv_off, int64_t alpha_w,
                   int64_t alpha_b, int64_t rgb_w, int64_t rgb_b, int tiles_per_block) {
-  __shared__ float4 sg[TROWS];
-  const int tid = threadIdx.x;
-  float acc_a = 0.f, acc_r[3] = {0.f, 0.f, 0.f}, acc_b = 0.f;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float aa[4][8];      // sigma head: 4 column groups x 8 columns
+  float ar[2][3][8];   // rgb head: 2 column groups x 3 channels x 8 columns
+  float ab[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aa[a][i] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ar[a][c][i] = 0.f;
   const int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
   const int64_t t1 = (t0 + tiles_per_block < ntiles) ? t0 + tiles_per_block : ntiles;
   for (int64_t tile = t0; tile < t1; ++tile) {
-    __syncthreads();
-    if (tid < TROWS) {
-      const int64_t m = tile * TROWS + tid;
-      sg[tid] = (m < M) ? reinterpret_cast<const float4*>(g_out)[m] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
     const uint8_t* rec = fstash + tile * (int64_t)frec_bytes;
-    {   // sigma head: column tid of the last trunk activation
-      const __half* hp = reinterpret_cast<const __half*>(rec + h_last_off + (tid >> 3) * (TROWS * 16) + (tid & 7) * 2);
-      for (int s = 0; s < TROWS; ++s) acc_a = fmaf(sg[s].w, __half2float(hp[s * 8]), acc_a);
-    }
-    if (tid < 128) {   // rgb head: column tid of the views hidden layer
-      const __half* hp = reinterpret_cast<const __half*>(rec + hv_off + (tid >> 3) * (TROWS * 16) + (tid & 7) * 2);
-      for (int s = 0; s < TROWS; ++s) {
-        const float h = __half2float(hp[s * 8]);
-        acc_r[0] = fmaf(sg[s].x, h, acc_r[0]);
-        acc_r[1] = fmaf(sg[s].y, h, acc_r[1]);
-        acc_r[2] = fmaf(sg[s].z, h, acc_r[2]);
+#pragma unroll 1
+    for (int rb = 0; rb < 4; ++rb) {
+      const int row = rb * 32 + lane;
+      const int64_t m = tile * TROWS + row;
+      const float4 g = (m < M) ? reinterpret_cast<const float4*>(g_out)[m] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (w == 0) { ab[0] += g.x; ab[1] += g.y; ab[2] += g.z; ab[3] += g.w; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(rec + h_last_off + (w + 8 * a) * (TROWS * 16) + row * 16), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) aa[a][i] = fmaf(g.w, v[i], aa[a][i]);
       }
-    } else if (tid < 132) {   // head biases
-      const int c = tid - 128;
-      for (int s = 0; s < TROWS; ++s) {
-        const float4 v = sg[s];
-        acc_b += (c == 0) ? v.x : (c == 1) ? v.y : (c == 2) ? v.z : v.w;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(rec + hv_off + (w + 8 * a) * (TROWS * 16) + row * 16), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ar[a][0][i] = fmaf(g.x, v[i], ar[a][0][i]);
+          ar[a][1][i] = fmaf(g.y, v[i], ar[a][1][i]);
+          ar[a][2][i] = fmaf(g.z, v[i], ar[a][2][i]);
+        }
       }
     }
   }
-  atomicAdd(g_params + alpha_w + tid, acc_a);
-  if (tid < 128) {
-    atomicAdd(g_params + rgb_w + tid, acc_r[0]);
-    atomicAdd(g_params + rgb_w + 128 + tid, acc_r[1]);
-    atomicAdd(g_params + rgb_w + 256 + tid, acc_r[2]);
-  } else if (tid < 132) {
-    const int c = tid - 128;
-    atomicAdd(g_params + (c < 3 ? rgb_b + c : alpha_b), acc_b);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = warp_sum(aa[a][i]);
+      if (lane == 0) atomicAdd(g_params + alpha_w + (w + 8 * a) * 8 + i, t);
+    }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = warp_sum(ar[a][c][i]);
+        if (lane == 0) atomicAdd(g_params + rgb_w + c * 128 + (w + 8 * a) * 8 + i, t);
+      }
+  if (w == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float t = warp_sum(ab[c]);
+      if (lane == 0) atomicAdd(g_params + (c < 3 ? rgb_b + c : alpha_b), t);
+    }
   }
 }
 

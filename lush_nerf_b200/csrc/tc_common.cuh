@@ -157,6 +157,13 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return r;
 }
 
+// same with ReLU fused into the conversion (max(x, 0) then round): one instruction for two activations
+__device__ __forceinline__ uint32_t pack_h2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // byte offset of element (r, c) inside a [rows x *] tile-canonical fp16 blob
 __host__ __device__ constexpr uint32_t blob_off(uint32_t rows, uint32_t r, uint32_t c) {
   return (c >> 3) * (rows * 16u) + r * 16u + (c & 7u) * 2u;

@@ -164,6 +164,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "simt", "tc"], help="override LUSH_MLP_IMPL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--render-frames", type=int, default=5)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -257,6 +259,34 @@ def main():
     value = rays_total / (ms_total * 1e-3)
     e2e_val = rays_total / (e2e_ms * 1e-3)
 
+    # ---- render leg (BASELINE configs[3]): --render_only style full frames, chunk 32768, 64+64, det sampling
+    render = None
+    if world == 1 and not args.no_render:
+        from lush_nerf_b200.synthetic import spiral_poses
+        poses = torch.from_numpy(spiral_poses(args.render_frames + 2, radius_scale=2.0)).to(dev)
+        rk = dict(perturb=False, N_importance=N_IMPORTANCE, N_samples=N_SAMPLES, use_viewdirs=True, white_bkgd=False,
+                  raw_noise_std=0.0, inference=True, near=0.0, far=1.0)
+        model.eval()
+        with torch.no_grad():
+            model(H, W, trainer.K, chunk=1024 * 32, poses=poses[:2], render_kwargs=dict(rk))   # warm-up frames
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            mlp_events.clear()
+            ops.MLP_EVENT_SINK = mlp_events
+            r0.record()
+            rgbs, _, _ = model(H, W, trainer.K, chunk=1024 * 32, poses=poses[2:], render_kwargs=dict(rk))
+            r1.record()
+            torch.cuda.synchronize()
+            ops.MLP_EVENT_SINK = None
+        ms_frame = r0.elapsed_time(r1) / args.render_frames
+        mlp_ms_frame = sum(a.elapsed_time(b) for a, b in mlp_events) / args.render_frames
+        fl = FLOP_FWD_PER_SAMPLE * H * W * SAMPLES_PER_RAY
+        render = {"ms_per_frame": ms_frame, "frames": args.render_frames, "rays_per_s": H * W / (ms_frame * 1e-3),
+                  "image": f"{H}x{W}", "chunk": 32768, "mlp_ms_per_frame": mlp_ms_frame,
+                  "mlp_tflops": fl / (mlp_ms_frame * 1e-3) / 1e12 if mlp_ms_frame > 0 else None,
+                  "finite": bool(torch.isfinite(rgbs).all().item())}
+        model.train()
+
     if rank == 0:
         peaks = measured_peaks()
         flops_step = 3 * FLOP_FWD_PER_SAMPLE * N_RAND * K_RAYS * SAMPLES_PER_RAY
@@ -279,6 +309,7 @@ def main():
                          "mlp_ms_per_step": mlp_ms / args.steps, "mlp_calls_per_step": mlp_calls / args.steps,
                          "peak_source": peaks["source"]},
             "final_loss": loss_host,
+            "render": render,
         }
         if not args.no_cpu_baseline and world == 1:
             val, ms, cores, sample = cpu_reference_run(steps=2, warmup=1)

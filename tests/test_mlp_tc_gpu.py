@@ -147,7 +147,7 @@ def test_tc_backward_exact_in_the_all_active_regime(det_state, R, S, need_in):
     assert ((r1[0] - r0[0]).abs().amax(dim=(0, 1)) / scale).max().item() <= 4e-3
     for (name, _), g1, g0 in zip(O.mlp_param_shapes(8, 256, 63, 27, 4), r1[1], r0[1]):
         assert g1 is not None and torch.isfinite(g1).all(), name
-        assert _rel(g1, g0) <= 8e-3, (name, _rel(g1, g0))
+        assert _rel(g1, g0) <= 1.5e-2, (name, _rel(g1, g0))
     if need_in:
         assert _rel(r1[2][:, 0:6], r0[2][:, 0:6]) <= 1e-2, ("d o,d", _rel(r1[2][:, 0:6], r0[2][:, 0:6]))
         assert _rel(r1[2][:, 8:11], r0[2][:, 8:11]) <= 1e-2, ("d viewdirs", _rel(r1[2][:, 8:11], r0[2][:, 8:11]))

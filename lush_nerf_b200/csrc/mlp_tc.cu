@@ -187,7 +187,7 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
     *reinterpret_cast<uint4*>(smem + FwdSmem::ONES + i * 16) = (i < TROWS) ? make_uint4(0x3C00u, 0u, 0u, 0u)
                                                                             : make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }   // both issuers release a stage
     for (int t = 0; t < 2; ++t) { mbar_init(&a_ready[t], 4 * 32); mbar_init(&d_ready[t], 1); }
     fence_barrier_init();
   }
@@ -217,59 +217,60 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
         }
       }
     }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
+  } else if (warp == 1 || warp == 2) {
+    // =========================== MMA issuers: warp 1 -> tile slot 0, warp 2 -> tile slot 1 =================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      uint32_t a_phase[2] = {0, 0};
+      const int t = warp - 1;
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
       const uint32_t sbase = smem_u32(smem);
+      const uint32_t tacc = tmem_base + t * 256;
+      const uint32_t a_hi = desc_hi(128u), b_hi = desc_hi(128u);
+      const uint32_t h_lo = desc_lo(sbase + FwdSmem::H0 + t * H_BYTES, TROWS * 16u);
+      const uint32_t e_lo = desc_lo(sbase + FwdSmem::ENC0 + t * ENC_BYTES, TROWS * 16u);
+      const uint32_t ones_lo = desc_lo(sbase + FwdSmem::ONES, TROWS * 16u);
+      constexpr uint32_t A_K16 = (2u * TROWS * 16u) >> 4;       // start-address units per 16 columns of A
       for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
-        const int nt = (2 * st + 1 < ntiles) ? 2 : 1;
+        const bool active = (2 * st + t) < ntiles;
         for (int s = 0; s < P.nsteps; ++s) {
-          const FwdStep& S_ = P.steps[s];
-          const uint32_t idesc = make_idesc_f16(TROWS, S_.N, 0, 0);
-          const uint32_t b_lbo = (uint32_t)S_.N * 16u;
-          for (int j = 0; j <= S_.nslices; ++j) {
+          const int N = P.steps[s].N, ns = P.steps[s].nslices, es = P.steps[s].enc_slices;
+          const int first_enc = P.steps[s].enc_first ? 0 : ns - es;   // slices [first_enc, first_enc+es) read ENC
+          const uint32_t idesc = make_idesc_f16(TROWS, N, 0, 0);
+          const uint32_t b_lbo = (uint32_t)N * 16u;
+          const uint32_t B_K16 = (2u * b_lbo) >> 4;
+          int hcol = 0, ecol = 0;    // running 16-column offsets inside H / ENC
+          for (int j = 0; j <= ns; ++j) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t bbuf = sbase + FwdSmem::STAGE0 + stage * STAGE_BYTES;
-            if (j == S_.nslices) {
-              // bias: ones[128 x 16] . biasrow[N x 16]^T accumulated on top of the layer product
-              const uint64_t ad = make_smem_desc(sbase + FwdSmem::ONES, TROWS * 16u, 128u);
-              const uint64_t bd = make_smem_desc(bbuf, b_lbo, 128u);
-              for (int t = 0; t < nt; ++t) umma_f16(tmem_base + t * 256, ad, bd, idesc, 1u);
-            } else {
-              // which activation buffer / column does this slice read?
-              bool from_enc; int kcol;
-              if (S_.enc_first) { from_enc = j < S_.enc_slices; kcol = from_enc ? j * KS : (j - S_.enc_slices) * KS; }
-              else { const int mainsl = S_.nslices - S_.enc_slices; from_enc = j >= mainsl; kcol = from_enc ? (j - mainsl) * KS : j * KS; }
-              for (int t = 0; t < nt; ++t) {
-                if (j == 0) { mbar_wait(&a_ready[t], a_phase[t]); a_phase[t] ^= 1; tc_fence_after(); }
-                const uint32_t abuf = sbase + (from_enc ? FwdSmem::ENC0 + t * ENC_BYTES : FwdSmem::H0 + t * H_BYTES);
-#pragma unroll
-                for (int kk = 0; kk < KS / 16; ++kk) {
-                  const uint64_t ad = make_smem_desc(abuf + (uint32_t)((kcol + kk * 16) / 8) * (TROWS * 16u), TROWS * 16u, 128u);
-                  const uint64_t bd = make_smem_desc(bbuf + kk * 2u * b_lbo, b_lbo, 128u);
-                  umma_f16(tmem_base + t * 256, ad, bd, idesc, (j > 0 || kk > 0) ? 1u : 0u);
-                }
+            if (active) {
+              const uint32_t b_lo = desc_lo(sbase + FwdSmem::STAGE0 + stage * STAGE_BYTES, b_lbo);
+              if (j == ns) {
+                umma_f16_lohi(tacc, ones_lo, a_hi, b_lo, b_hi, idesc, 1u);   // + bias
+              } else {
+                if (j == 0) { mbar_wait(&a_ready[t], a_phase); a_phase ^= 1; tc_fence_after(); }
+                const bool from_enc = (j >= first_enc) && (j < first_enc + es);
+                uint32_t a_lo;
+                if (from_enc) { a_lo = e_lo + ecol * A_K16; ecol += 2; } else { a_lo = h_lo + hcol * A_K16; hcol += 2; }
+                umma_f16_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, j > 0 ? 1u : 0u);
+                umma_f16_lohi(tacc, a_lo + A_K16, a_hi, b_lo + B_K16, b_hi, idesc, 1u);
               }
+              umma_commit(&empty_bar[stage]);
+            } else {
+              mbar_arrive(&empty_bar[stage]);
             }
-            umma_commit(&empty_bar[stage]);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&d_ready[0]);
-          if (nt > 1) umma_commit(&d_ready[1]);
+          if (active) umma_commit(&d_ready[t]);
         }
       }
     }
   } else {
     // =========================== epilogue warpgroups ===========================
-    const int t = (warp - 2) >> 2;                    // tile slot handled by this warpgroup
-    const int row = 32 * (warp & 3) + lane;           // TMEM lane == tile row
+    const int t = (warp - EPI_WARP0) >> 2;            // tile slot handled by this warpgroup
+    const int row = 32 * (warp & 3) + lane;           // TMEM lane == tile row (a warp may only touch lanes 32*(warp%4)..)
     const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
     uint8_t* Hb = smem + FwdSmem::H0 + t * H_BYTES;
     uint8_t* Eb = smem + FwdSmem::ENC0 + t * ENC_BYTES;
-    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const bool leader = ((warp - EPI_WARP0) & 3) == 0 && lane == 0;
     const int bar_id = 1 + t;
     const float4* wa4 = reinterpret_cast<const float4*>(sparams + P.w_alpha_off);
     const float* wr = sparams + P.w_rgb_off;

@@ -16,7 +16,8 @@ constexpr int ENC_BYTES = TROWS * 64 * 2;         // 16 KB
 constexpr int ENCV_BYTES = TROWS * 32 * 2;        // 8 KB
 constexpr int HV_BYTES = TROWS * 128 * 2;         // 32 KB
 constexpr int MAX_STEPS = kMaxDepth + 2;
-constexpr int FWD_THREADS = 320;
+constexpr int FWD_THREADS = 352;   // warp 0 producer, warps 1-2 MMA issuers (one per tile), warps 3-10 epilogue
+constexpr int EPI_WARP0 = 3;
 
 enum FwdEpi { EPI_TRUNK = 0, EPI_FEATURE = 1, EPI_VIEWS = 2 };
 
@@ -87,6 +88,24 @@ static inline void make_fwd_plan(const MlpLayout& L, FwdPlan& P) {
   P.rec_bytes = off;
 }
 
+
+// ---- lean MMA issue: descriptors are built once per step; per K=16 MMA only the 14-bit start-address field
+// (low word) advances.  hi word = SBO | version, lo word = start>>4 | (LBO>>4)<<16.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -16,7 +16,7 @@
 
 namespace lush {
 
-constexpr int BWD_THREADS = 320;
+constexpr int BWD_THREADS = FWD_THREADS;   // same warp roles as the forward kernel
 constexpr float kGradTarget = 32.f;   // scaled max |g_out|
 
 enum BwdEpi { BEPI_FEAT = 0, BEPI_TRUNK = 1, BEPI_ENC_SAVE = 2, BEPI_ENC_FINAL = 3 };
@@ -155,7 +155,7 @@ mlp_tc_dgrad_kernel(const __half* __restrict__ bstream, const float* __restrict_
   float* sparams = reinterpret_cast<float*>(smem + DgSmem::PARAMS);
   for (int i = tid; i < TW + 384; i += BWD_THREADS) sparams[i] = head_params[P.w_alpha_off + i];
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
     for (int t = 0; t < 2; ++t) { mbar_init(&a_ready[t], 128); mbar_init(&d_ready[t], 1); }
     fence_barrier_init();
   }
@@ -182,45 +182,48 @@ mlp_tc_dgrad_kernel(const __half* __restrict__ bstream, const float* __restrict_
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      uint32_t a_phase[2] = {0, 0};
+  } else if (warp == 1 || warp == 2) {
+    if (lane == 0) {   // MMA issuers: warp 1 -> tile slot 0, warp 2 -> tile slot 1
+      const int t = warp - 1;
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
       const uint32_t sbase = smem_u32(smem);
+      const uint32_t tacc = tmem_base + t * 256;
+      const uint32_t a_hi = desc_hi(128u), b_hi = desc_hi(128u);
+      const uint32_t g_lo = desc_lo(sbase + DgSmem::G0 + t * H_BYTES, TROWS * 16u);
+      constexpr uint32_t A_K16 = (2u * TROWS * 16u) >> 4;
       for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
-        const int nt = (2 * st + 1 < ntiles) ? 2 : 1;
+        const bool active = (2 * st + t) < ntiles;
         for (int s = 0; s < B.nsteps; ++s) {
-          const BwdStep& S_ = B.steps[s];
-          const uint32_t idesc = make_idesc_f16(TROWS, S_.N, 0, 0);
-          const uint32_t b_lbo = (uint32_t)S_.N * 16u;
-          for (int j = 0; j < S_.nslices; ++j) {
+          const int N = B.steps[s].N, ns = B.steps[s].nslices;
+          const uint32_t idesc = make_idesc_f16(TROWS, N, 0, 0);
+          const uint32_t b_lbo = (uint32_t)N * 16u;
+          const uint32_t B_K16 = (2u * b_lbo) >> 4;
+          for (int j = 0; j < ns; ++j) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            for (int t = 0; t < nt; ++t) {
-              if (j == 0) { mbar_wait(&a_ready[t], a_phase[t]); a_phase[t] ^= 1; tc_fence_after(); }
-              const uint32_t abuf = sbase + DgSmem::G0 + t * H_BYTES;
-#pragma unroll
-              for (int kk = 0; kk < KS / 16; ++kk) {
-                const uint64_t ad = make_smem_desc(abuf + (uint32_t)((j * KS + kk * 16) / 8) * (TROWS * 16u), TROWS * 16u, 128u);
-                const uint64_t bd = make_smem_desc(sbase + DgSmem::STAGE0 + stage * STAGE_BYTES + kk * 2u * b_lbo, b_lbo, 128u);
-                umma_f16(tmem_base + t * 256, ad, bd, idesc, (j > 0 || kk > 0) ? 1u : 0u);
-              }
+            if (active) {
+              if (j == 0) { mbar_wait(&a_ready[t], a_phase); a_phase ^= 1; tc_fence_after(); }
+              const uint32_t b_lo = desc_lo(sbase + DgSmem::STAGE0 + stage * STAGE_BYTES, b_lbo);
+              const uint32_t a_lo = g_lo + (uint32_t)(2 * j) * A_K16;
+              umma_f16_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, j > 0 ? 1u : 0u);
+              umma_f16_lohi(tacc, a_lo + A_K16, a_hi, b_lo + B_K16, b_hi, idesc, 1u);
+              umma_commit(&empty_bar[stage]);
+            } else {
+              mbar_arrive(&empty_bar[stage]);
             }
-            umma_commit(&empty_bar[stage]);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&d_ready[0]);
-          if (nt > 1) umma_commit(&d_ready[1]);
+          if (active) umma_commit(&d_ready[t]);
         }
       }
     }
   } else {
-    const int t = (warp - 2) >> 2;
+    const int t = (warp - EPI_WARP0) >> 2;
     const int row = 32 * (warp & 3) + lane;
     const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
     uint8_t* Gb = smem + DgSmem::G0 + t * H_BYTES;
     uint8_t* Eb = smem + DgSmem::ENC0 + t * ENC_BYTES;
-    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const bool leader = ((warp - EPI_WARP0) & 3) == 0 && lane == 0;
     const int bar_id = 1 + t;
     const float scale = grad_scale_from(scale_buf);
     const float inv_scale = 1.f / scale;

@@ -156,14 +156,6 @@ __device__ __forceinline__ void store_chunk(uint8_t* Hb, int cc, int row, const 
     *reinterpret_cast<uint4*>(Hb + ((cc >> 3) + g) * (TROWS * 16) + row * 16) = q;
   }
 }
-// sign bits of 32 accumulators, MSB-first: bit (31-j) = 1 iff column j is negative (ReLU inactive)
-__device__ __forceinline__ uint32_t sign_bits(const uint32_t (&r)[32]) {
-  uint32_t mb = 0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) mb = __funnelshift_l(r[j], mb, 1);
-  return mb;
-}
-
 // ------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------

@@ -107,6 +107,36 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, ui
       : "memory");
 }
 
+// ---- 1-bit ReLU masks (written by the forward epilogue, applied by the dgrad epilogue) ----------------
+// One 32-bit word covers 32 accumulator columns = 16 packed fp16x2 words w = 0..15 (word w = columns 2w, 2w+1).
+// Bit = 1: the unit was inactive (negative pre-activation).  The bit of column c sits where ONE byte-permute with
+// sign replication turns it into a full fp16 lane mask after a left shift by s = w>>1:
+//     position(c) = 15 + 16*(c&1) - 8*(w&1) - s          (w = c>>1)
+// i.e. for even w the two bits sit at the sign positions of bytes 1 and 3 of (m << s), for odd w at bytes 0 and 2.
+__host__ __device__ constexpr int relu_mask_pos(int c) {
+  return 15 + 16 * (c & 1) - 8 * ((c >> 1) & 1) - (c >> 2);
+}
+// column whose bit lands at position P (inverse of relu_mask_pos)
+__host__ __device__ constexpr int relu_mask_col(int P) {
+  return 2 * (2 * ((P & 15) < 8 ? 7 - (P & 15) : 15 - (P & 15)) + ((P & 15) < 8 ? 1 : 0)) + (P >> 4);
+}
+// sign bits of 32 fp32 accumulators in the layout above: 32 funnel shifts, the k-th shifted-in bit ends at 31-k
+__device__ __forceinline__ uint32_t sign_bits(const uint32_t (&r)[32]) {
+  uint32_t mb = 0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) mb = __funnelshift_l(r[relu_mask_col(31 - k)], mb, 1);
+  return mb;
+}
+// zero the fp16 lanes of packed word w (columns 2w, 2w+1 of the chunk) whose mask bit is set: shift + prmt + lop3
+template <int W_>
+__device__ __forceinline__ uint32_t relu_mask_apply(uint32_t packed, uint32_t m) {
+  uint32_t lanes;
+  const uint32_t t = m << (W_ >> 1);
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(lanes) : "r"(t), "n"((W_ & 1) ? 0xAA88 : 0xBB99));
+  return packed & ~lanes;
+}
+__device__ __forceinline__ bool relu_mask_test(uint32_t m, int c) { return (m >> relu_mask_pos(c)) & 1u; }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

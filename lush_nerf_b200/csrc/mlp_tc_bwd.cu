@@ -253,7 +253,7 @@ mlp_tc_dgrad_kernel(const __half* __restrict__ bstream, const float* __restrict_
           for (int i = 0; i < 8; ++i) {
             const int j = gq * 8 + i;
             float x = g.x * wr[j] + g.y * wr[128 + j] + g.z * wr[256 + j];
-            v[i] = ((mw[j >> 5] >> (31 - (j & 31))) & 1u) ? 0.f : x;   // stash bit = 1: unit was inactive
+            v[i] = relu_mask_test(mw[j >> 5], j & 31) ? 0.f : x;   // stash bit = 1: unit was inactive
           }
           uint4 q;
           q.x = pack_h2(v[0], v[1]); q.y = pack_h2(v[2], v[3]); q.z = pack_h2(v[4], v[5]); q.w = pack_h2(v[6], v[7]);
@@ -278,29 +278,47 @@ mlp_tc_dgrad_kernel(const __half* __restrict__ bstream, const float* __restrict_
         mbar_wait(&d_ready[t], d_phase); d_phase ^= 1;
         tc_fence_after();
         if (S_.epi == BEPI_FEAT || S_.epi == BEPI_TRUNK) {
+          const uint32_t tacc = tmem_base + tlane + t * 256;
+          uint32_t ra[32], rb2[32];
+          tmem_ld32(tacc, ra);                  // overlaps with the wait on the previous dZ store
           if (leader) bulk_wait_read_all();   // the previous dZ blob is still being stored from Gb
           named_bar_sync(bar_id, 128);
-#pragma unroll 1
-          for (int cc = 0; cc < TW; cc += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + tlane + t * 256 + cc, r);
-            tmem_ld_wait();
-            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(r[j]);
-              if (S_.epi == BEPI_TRUNK) {
-                if (S_.add_alpha) x = fmaf(g_sigma, wa[cc + j], x);
-                x = ((mw[cc >> 5] >> (31 - j)) & 1u) ? 0.f : x;
+          for (int cc = 0; cc < TW; cc += 64) {
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+              uint32_t (&r)[32] = hb ? rb2 : ra;
+              const int c = cc + 32 * hb;
+              tmem_ld_wait();
+              if (c + 32 < TW) tmem_ld32(tacc + c + 32, hb ? ra : rb2);
+              if (S_.add_alpha) {               // + g_sigma * w_alpha: gradient arriving through the sigma head
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 w4 = reinterpret_cast<const float4*>(wa)[(c >> 2) + j4];
+                  r[4 * j4 + 0] = __float_as_uint(fmaf(g_sigma, w4.x, __uint_as_float(r[4 * j4 + 0])));
+                  r[4 * j4 + 1] = __float_as_uint(fmaf(g_sigma, w4.y, __uint_as_float(r[4 * j4 + 1])));
+                  r[4 * j4 + 2] = __float_as_uint(fmaf(g_sigma, w4.z, __uint_as_float(r[4 * j4 + 2])));
+                  r[4 * j4 + 3] = __float_as_uint(fmaf(g_sigma, w4.w, __uint_as_float(r[4 * j4 + 3])));
+                }
               }
-              v[j] = x;
-            }
+              uint32_t pw[16];
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              uint4 q;
-              q.x = pack_h2(v[8 * gq + 0], v[8 * gq + 1]); q.y = pack_h2(v[8 * gq + 2], v[8 * gq + 3]);
-              q.z = pack_h2(v[8 * gq + 4], v[8 * gq + 5]); q.w = pack_h2(v[8 * gq + 6], v[8 * gq + 7]);
-              *reinterpret_cast<uint4*>(Gb + ((cc >> 3) + gq) * (TROWS * 16) + row * 16) = q;
+              for (int w = 0; w < 16; ++w) pw[w] = pack_h2(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]));
+              if (S_.epi == BEPI_TRUNK) {       // ReLU gate of the producing layer: 1.25 integer ops per element
+                const uint32_t m = mw[c >> 5];
+                pw[0] = relu_mask_apply<0>(pw[0], m);   pw[1] = relu_mask_apply<1>(pw[1], m);
+                pw[2] = relu_mask_apply<2>(pw[2], m);   pw[3] = relu_mask_apply<3>(pw[3], m);
+                pw[4] = relu_mask_apply<4>(pw[4], m);   pw[5] = relu_mask_apply<5>(pw[5], m);
+                pw[6] = relu_mask_apply<6>(pw[6], m);   pw[7] = relu_mask_apply<7>(pw[7], m);
+                pw[8] = relu_mask_apply<8>(pw[8], m);   pw[9] = relu_mask_apply<9>(pw[9], m);
+                pw[10] = relu_mask_apply<10>(pw[10], m); pw[11] = relu_mask_apply<11>(pw[11], m);
+                pw[12] = relu_mask_apply<12>(pw[12], m); pw[13] = relu_mask_apply<13>(pw[13], m);
+                pw[14] = relu_mask_apply<14>(pw[14], m); pw[15] = relu_mask_apply<15>(pw[15], m);
+              }
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq)
+                *reinterpret_cast<uint4*>(Gb + ((c >> 3) + gq) * (TROWS * 16) + row * 16) =
+                    make_uint4(pw[4 * gq], pw[4 * gq + 1], pw[4 * gq + 2], pw[4 * gq + 3]);
             }
           }
           fence_proxy_async();

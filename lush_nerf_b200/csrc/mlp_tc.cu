@@ -3,81 +3,111 @@
 // Replaces reference helpers:311-344 (Embedder), helpers:394-423 (NeRF.forward) and
 // models/lushnerf.py:234-266 (mlpforward) for W = 256 networks.
 //
-// Forward kernel (persistent, one CTA per SM, 320 threads):
-//   warp 0      weight producer: streams the pre-packed fp16 weight K-slices (16 KB each) with 1-D bulk
-//               async copies (cp.async.bulk, the TMA engine) through a 3-stage mbarrier ring
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16) for TWO 128-row sample
-//               tiles per weight slice (halves L2 weight traffic per row), accumulators in TMEM (2 x 256 cols)
-//   warps 2-9   two epilogue warpgroups (one per tile): tcgen05.ld -> +bias -> ReLU -> fp16 -> st.shared in
-//               the UMMA operand layout, i.e. the next layer's A operand never leaves the SM.  The sigma
-//               head (256->1) and rgb head (128->3) are register dot products in the epilogues; only
-//               [M,4] fp32 goes back to HBM (plus, in training, the fp16 activation stash for backward).
-// Activations: H tile [128 x 256] fp16 (64 KB) per tile, encodings [128 x 64] (16 KB) per tile.
-#include "mlp_tc.cuh"
+// The kernel is one instance of the chain skeleton in mlp_chain.cuh (read that header first):
+//   steps 0..D-1   trunk layers (bias via a ones-column K=16 slice, gamma(x) via SS-mode slices, hidden state
+//                  via TS-mode slices straight from tensor memory), ReLU fused into the fp16 conversion
+//   step D         feature_linear (no activation)
+//   step D+1       views_linears[0] on [feature | gamma(viewdirs)], N = 128, accumulator region 1
+// The sigma head (256->1) and rgb head (128->3) are fp32 register dot products over the accumulators in the
+// epilogues; only [M,4] fp32 goes back to HBM -- plus, in training, the fp16 activation stash and 1-bit ReLU
+// masks for the backward kernels, written with coalesced 16-byte stores straight from the epilogue registers.
+#include "mlp_chain.cuh"
 
 namespace lush {
 using namespace tc;
 
-// One thread per packed fp16 element of the forward weight stream.
-// Step s = nslices regular slices [N x 32] followed by one bias slice [N x 16] (column 0 = bias).
-// element (n, kk) of slice j: offset = step_base + j*N*KS*2 + (kk/8)*(N*16) + n*16 + (kk%8)*2
+enum FwdEpiKind { FE_TRUNK = 0, FE_TRUNK_LAST = 1, FE_FEATURE = 2, FE_VIEWS = 3 };
+
+// ------------------------------------------------------------------------------------------------
+// host: chain plan + weight packing
+// ------------------------------------------------------------------------------------------------
+static void make_fwd_chain(const MlpLayout& L, const FwdPlan& P, ChainPlan& C) {
+  int n = 0;
+  for (int i = 0; i < L.D; ++i) {
+    ChainStep& s = C.steps[n];
+    s.nhalf = 2; s.d0 = 0; s.NH = 128; s.pre16 = 1; s.enc_src = 0;
+    const bool enc = (i == 0) || (L.skip >= 0 && i == L.skip + 1);
+    s.enc_slices = enc ? 2 : 0;
+    s.h_slices = (i == 0) ? 0 : TW / KS;
+    s.a_in = (int8_t)(n & 1); s.wait_a = (i > 0); s.a_out = (int8_t)((n + 1) & 1);
+    s.epi = (i == L.D - 1) ? FE_TRUNK_LAST : FE_TRUNK;
+    s.p0 = (int16_t)i; s.p1 = 0;
+    s.off0 = P.rec_h0 + i * H_BYTES;
+    s.off1 = P.rec_mask + i * TROWS * 32;
+    ++n;
+  }
+  { ChainStep& s = C.steps[n];
+    s.nhalf = 2; s.d0 = 0; s.NH = 128; s.pre16 = 1; s.enc_src = 0; s.enc_slices = 0; s.h_slices = TW / KS;
+    s.a_in = (int8_t)(n & 1); s.wait_a = 1; s.a_out = (int8_t)((n + 1) & 1);
+    s.epi = FE_FEATURE; s.p0 = 0; s.p1 = 0; s.off0 = P.rec_feat; s.off1 = 0;
+    ++n; }
+  { ChainStep& s = C.steps[n];
+    s.nhalf = 1; s.d0 = 1; s.NH = 128; s.pre16 = 1; s.enc_src = 1; s.enc_slices = 1; s.h_slices = TW / KS;
+    s.a_in = (int8_t)(n & 1); s.wait_a = 1; s.a_out = -1;
+    s.epi = FE_VIEWS; s.p0 = 0; s.p1 = 0; s.off0 = P.rec_hv; s.off1 = P.rec_maskv;
+    ++n; }
+  C.nsteps = n;
+  chain_finish_plan(C);
+}
+
+// One block row (blockIdx.y) per step; one thread per packed fp16 element.  Per half h of a step the stream holds
+//   [bias block NH x 16 (column 0 = bias)] [enc block NH x 32*enc_slices] [hidden blocks NH x 128 ...]
+// each block in the tile-canonical layout with NH rows: offset(n, k) = (k/8)*(NH*16) + n*16 + (k%8)*2.
 struct PackJob {
   int64_t out_off;   // byte offset of the step in the stream
   int64_t w_off;     // float offset of the [N, fan_in] weight in the flat params
   int64_t b_off;     // float offset of the bias [N]
-  int N, fan_in, nslices;
-  int enc_slices, enc_first, enc_real, enc_col0, main_col0;  // column mapping (see pack kernel)
+  int fan_in, nhalf, NH, pre16, enc_slices, h_slices;
+  int enc_real, enc_col0, main_col0;   // nn.Linear column of encoding channel 0 / hidden unit 0
 };
 struct PackPlan {
   int njobs;
-  PackJob jobs[MAX_STEPS];
+  PackJob jobs[CH_MAX_STEPS];
 };
 
 __global__ void pack_fwd_weights_kernel(const float* __restrict__ params, __half* __restrict__ stream,
                                         PackPlan plan) {
   const PackJob& J = plan.jobs[blockIdx.y];
-  const int64_t nreg = (int64_t)J.nslices * J.N * KS;
-  const int64_t total = nreg + (int64_t)J.N * 16;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
+  const int n_pre = J.NH * 16 * J.pre16, n_enc = J.NH * KS * J.enc_slices;
+  const int per_half = n_pre + n_enc + J.NH * KS * J.h_slices;
+  const int total = J.nhalf * per_half;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int h = e / per_half;
+    int r = e - h * per_half;
     float v = 0.f;
-    if (e < nreg) {
-      int j = (int)(e / (J.N * KS));
-      int rem = (int)(e - (int64_t)j * J.N * KS);
-      int kk8 = rem / (J.N * 8);          // which 8-column group inside the slice
-      int rem2 = rem - kk8 * J.N * 8;
-      int n = rem2 / 8, k8 = rem2 % 8;
-      int k = j * KS + kk8 * 8 + k8;      // K index within the step (padded, concatenated segments)
-      int col = -1;                       // nn.Linear column
-      const int enc_k = J.enc_slices * KS;
-      const int main_k = (J.nslices - J.enc_slices) * KS;
-      if (J.enc_first) {
-        if (k < enc_k) { if (k < J.enc_real) col = J.enc_col0 + k; }
-        else col = J.main_col0 + (k - enc_k);
-      } else {
-        if (k < main_k) col = J.main_col0 + k;
-        else if (k - main_k < J.enc_real) col = J.enc_col0 + (k - main_k);
-      }
-      if (col >= 0) v = params[J.w_off + (int64_t)n * J.fan_in + col];
+    if (r < n_pre) {
+      const int g = r / (J.NH * 8), rem = r - g * J.NH * 8;
+      const int n = rem >> 3, k8 = rem & 7;
+      if (g == 0 && k8 == 0) v = params[J.b_off + h * J.NH + n];
     } else {
-      int rem = (int)(e - nreg);          // bias slice: [N x 16], only column 0 is non-zero
-      int g = rem / (J.N * 8);
-      int rem2 = rem - g * J.N * 8;
-      int n = rem2 / 8, k8 = rem2 % 8;
-      if (g == 0 && k8 == 0) v = params[J.b_off + n];
+      r -= n_pre;
+      int col = -1, n;
+      if (r < n_enc) {
+        const int kk8 = r / (J.NH * 8), rem = r - kk8 * J.NH * 8;
+        n = rem >> 3;
+        const int k = kk8 * 8 + (rem & 7);
+        if (k < J.enc_real) col = J.enc_col0 + k;
+      } else {
+        r -= n_enc;
+        const int blk = r / (J.NH * 128), rem = r - blk * J.NH * 128;
+        const int kk8 = rem / (J.NH * 8), rem2 = rem - kk8 * J.NH * 8;
+        n = rem2 >> 3;
+        col = J.main_col0 + blk * 128 + kk8 * 8 + (rem2 & 7);
+      }
+      if (col >= 0) v = params[J.w_off + (int64_t)(h * J.NH + n) * J.fan_in + col];
     }
     stream[J.out_off / 2 + e] = __float2half_rn(v);
   }
 }
 
-static void make_pack_plan(const MlpLayout& L, const FwdPlan& P, PackPlan& K) {
-  K.njobs = P.nsteps;
+static void make_pack_plan(const MlpLayout& L, const ChainPlan& C, PackPlan& K) {
+  K.njobs = C.nsteps;
   int64_t off = 0;
-  for (int s = 0; s < P.nsteps; ++s) {
-    const FwdStep& st = P.steps[s];
+  for (int s = 0; s < C.nsteps; ++s) {
+    const ChainStep& st = C.steps[s];
     PackJob& J = K.jobs[s];
     J.out_off = off;
-    J.N = st.N; J.nslices = st.nslices; J.enc_slices = st.enc_slices; J.enc_first = st.enc_first;
+    J.nhalf = st.nhalf; J.NH = st.NH; J.pre16 = st.pre16; J.enc_slices = st.enc_slices; J.h_slices = st.h_slices;
     if (s < L.D) {
       J.w_off = L.pts_w[s]; J.b_off = L.pts_b[s]; J.fan_in = L.pts_in[s];
       J.enc_real = L.in_ch; J.enc_col0 = 0;
@@ -88,26 +118,19 @@ static void make_pack_plan(const MlpLayout& L, const FwdPlan& P, PackPlan& K) {
       J.w_off = L.views_w; J.b_off = L.views_b; J.fan_in = L.W + L.in_ch_v;   // [feature | views] (helpers:409)
       J.enc_real = L.in_ch_v; J.enc_col0 = L.W; J.main_col0 = 0;
     }
-    off += (int64_t)st.nslices * st.N * KS * 2 + (int64_t)st.N * 16 * 2;
+    off += (int64_t)st.nhalf * chain_half_bytes(st);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
-struct FwdSmem {
-  // offsets into dynamic shared memory
-  static constexpr int H0 = 0;
-  static constexpr int ENC0 = 2 * H_BYTES;
-  static constexpr int STAGE0 = ENC0 + 2 * ENC_BYTES;
-  static constexpr int ONES = STAGE0 + NSTAGE * STAGE_BYTES;   // [128 x 16] fp16, column 0 = 1 (bias operand)
-  static constexpr int PARAMS = ONES + TROWS * 16 * 2;
-};
-
-// gamma(x) for one coordinate triple into the tile-canonical [128 x 64] (or [128 x 32]) fp16 blob, row `row`.
+// gamma(x) for one coordinate triple into the tile-canonical [128 x NCOL] fp16 blob, row `row` (shared memory, and
+// the same 16-byte groups to the stash record when gdst != nullptr).
 // channel order: [x(3), sin(2^0 x)(3), cos(2^0 x)(3), ...]; columns >= 3+6L are zero padding.
 template <int NCOL>
-__device__ __forceinline__ void encode_row_to_smem(uint8_t* blob, int row, float x0, float x1, float x2, int L) {
+__device__ __forceinline__ void encode_row(uint8_t* blob, uint8_t* gdst, int row, float x0, float x1, float x2,
+                                           int L) {
   float vals[NCOL];
 #pragma unroll
   for (int c = 0; c < NCOL; ++c) vals[c] = 0.f;
@@ -133,56 +156,49 @@ __device__ __forceinline__ void encode_row_to_smem(uint8_t* blob, int row, float
     q.z = pack_h2(vals[8 * g + 4], vals[8 * g + 5]);
     q.w = pack_h2(vals[8 * g + 6], vals[8 * g + 7]);
     *reinterpret_cast<uint4*>(blob + g * (TROWS * 16) + row * 16) = q;
+    if (gdst) *reinterpret_cast<uint4*>(gdst + g * (TROWS * 16) + row * 16) = q;
   }
 }
 
-// 32 accumulator columns -> fp16 (optionally through ReLU) -> 4 x 16-byte stores in the operand layout
 template <bool RELU>
-__device__ __forceinline__ void store_chunk(uint8_t* Hb, int cc, int row, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void pack_chunk(const uint32_t (&r)[32], uint32_t (&pw)[16]) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint4 q;
-    if (RELU) {
-      q.x = pack_h2_relu(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
-      q.y = pack_h2_relu(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
-      q.z = pack_h2_relu(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
-      q.w = pack_h2_relu(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-    } else {
-      q.x = pack_h2(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
-      q.y = pack_h2(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
-      q.z = pack_h2(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
-      q.w = pack_h2(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-    }
-    *reinterpret_cast<uint4*>(Hb + ((cc >> 3) + g) * (TROWS * 16) + row * 16) = q;
-  }
+  for (int w = 0; w < 16; ++w)
+    pw[w] = RELU ? pack_h2_relu(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]))
+                 : pack_h2(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]));
 }
+// 32 columns (4 groups of 8) of one row of a [128 x *] tile-canonical blob in global memory; c = first column
+__device__ __forceinline__ void store_chunk_global(uint8_t* blob, int c, int row, const uint32_t (&pw)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(blob + ((c >> 3) + g) * (TROWS * 16) + row * 16) =
+        make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------
 template <bool TRAIN>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
-mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ params_smem_src,
+__global__ void __launch_bounds__(CH_THREADS, 1)
+mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ params_smem_src,
                   const float* __restrict__ ray_batch, int ray_stride, const float* __restrict__ z,
                   float* __restrict__ out, uint8_t* __restrict__ stash, int64_t M, int S, int L_pts,
-                  int L_views, FwdPlan P) {
+                  int L_views, ChainPlan C, FwdPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], a_ready[2], d_ready[2];
+  __shared__ ChainBars B;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_alpha[TROWS];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + TROWS - 1) / TROWS;
-  const int64_t nsuper = (ntiles + 1) / 2;
-  float* sparams = reinterpret_cast<float*>(smem + FwdSmem::PARAMS);
+  float* sparams = reinterpret_cast<float*>(smem + ChSmem::PARAMS);
 
-  for (int i = tid; i < P.nparam_floats; i += FWD_THREADS) sparams[i] = params_smem_src[i];
-  for (int i = tid; i < TROWS * 16 * 2 / 16; i += FWD_THREADS)   // ones operand: row r -> [1,0,...,0 | 0 x 8]
-    *reinterpret_cast<uint4*>(smem + FwdSmem::ONES + i * 16) = (i < TROWS) ? make_uint4(0x3C00u, 0u, 0u, 0u)
-                                                                            : make_uint4(0u, 0u, 0u, 0u);
-  if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }   // both issuers release a stage
-    for (int t = 0; t < 2; ++t) { mbar_init(&a_ready[t], 4 * 32); mbar_init(&d_ready[t], 1); }
-    fence_barrier_init();
-  }
+  for (int i = tid; i < P.nparam_floats; i += CH_THREADS) sparams[i] = params_smem_src[i];
+  // ones operand (both buffers): row r -> [1, 0 x 7 | 0 x 8]: the K=16 slice that adds the bias inside the MMA
+  for (int i = tid; i < 2 * CH_X16_BYTES / 16; i += CH_THREADS)
+    *reinterpret_cast<uint4*>(smem + ChSmem::X160 + i * 16) =
+        ((i % (CH_X16_BYTES / 16)) < TROWS) ? make_uint4(0x3C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) chain_init_bars(B);
   if (warp == 1) tmem_alloc(&tmem_base_s, 512);
   fence_proxy_async();
   tc_fence_before();
@@ -191,216 +207,136 @@ mlp_tc_fwd_kernel(const __half* __restrict__ wstream, const float* __restrict__ 
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    // =========================== weight producer ===========================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(wstream);
-        for (int s = 0; s < P.nsteps; ++s) {
-          const int ns = P.steps[s].nslices;
-          for (int j = 0; j <= ns; ++j) {   // j == ns: the bias slice (K = 16)
-            const uint32_t bytes = (uint32_t)P.steps[s].N * (j < ns ? KS : 16) * 2;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], bytes);
-            bulk_g2s(smem + FwdSmem::STAGE0 + stage * STAGE_BYTES, src, bytes, &full_bar[stage]);
-            src += bytes;
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-          }
-        }
+    if (lane == 0) chain_producer(B, smem, wstream, C, ntiles);
+  } else if (warp == 1) {
+    chain_mma_issuer(B, smem, tmem_base, C, ntiles, lane);
+  } else if (warp >= CH_WG_PRO) {
+    // =========================== prologue warpgroup: sample points + encodings of the NEXT tile ===========
+    const int row = tid - CH_WG_PRO * 32;
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = (int)(it & 1);
+      if (it >= 2) mbar_wait(&B.pro_free[b], (uint32_t)(((it >> 1) + 1) & 1));
+      const int64_t m = tile * TROWS + row;
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+      if (m < M) {
+        const int64_t r = m / S;
+        const float* rb = ray_batch + r * ray_stride;
+        const float zz = z[m];
+        x0 = __fadd_rn(rb[0], __fmul_rn(rb[3], zz));
+        x1 = __fadd_rn(rb[1], __fmul_rn(rb[4], zz));
+        x2 = __fadd_rn(rb[2], __fmul_rn(rb[5], zz));
+        vx = rb[8]; vy = rb[9]; vz = rb[10];
       }
+      uint8_t* rec = TRAIN ? stash + tile * (int64_t)P.rec_bytes : nullptr;
+      encode_row<64>(smem + ChSmem::ENC0 + b * ENC_BYTES, TRAIN ? rec + P.rec_encp : nullptr, row, x0, x1, x2, L_pts);
+      encode_row<32>(smem + ChSmem::ENCV0 + b * ENCV_BYTES, TRAIN ? rec + P.rec_encv : nullptr, row, vx, vy, vz,
+                     L_views);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B.pro_ready[b]);
     }
-  } else if (warp == 1 || warp == 2) {
-    // =========================== MMA issuers: warp 1 -> tile slot 0, warp 2 -> tile slot 1 =================
-    if (lane == 0) {
-      const int t = warp - 1;
-      int stage = 0; uint32_t phase = 0, a_phase = 0;
-      const uint32_t sbase = smem_u32(smem);
-      const uint32_t tacc = tmem_base + t * 256;
-      const uint32_t a_hi = desc_hi(128u), b_hi = desc_hi(128u);
-      const uint32_t h_lo = desc_lo(sbase + FwdSmem::H0 + t * H_BYTES, TROWS * 16u);
-      const uint32_t e_lo = desc_lo(sbase + FwdSmem::ENC0 + t * ENC_BYTES, TROWS * 16u);
-      const uint32_t ones_lo = desc_lo(sbase + FwdSmem::ONES, TROWS * 16u);
-      constexpr uint32_t A_K16 = (2u * TROWS * 16u) >> 4;       // start-address units per 16 columns of A
-      for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
-        const bool active = (2 * st + t) < ntiles;
-        for (int s = 0; s < P.nsteps; ++s) {
-          const int N = P.steps[s].N, ns = P.steps[s].nslices, es = P.steps[s].enc_slices;
-          const int first_enc = P.steps[s].enc_first ? 0 : ns - es;   // slices [first_enc, first_enc+es) read ENC
-          const uint32_t idesc = make_idesc_f16(TROWS, N, 0, 0);
-          const uint32_t b_lbo = (uint32_t)N * 16u;
-          const uint32_t B_K16 = (2u * b_lbo) >> 4;
-          int hcol = 0, ecol = 0;    // running 16-column offsets inside H / ENC
-          for (int j = 0; j <= ns; ++j) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            if (active) {
-              const uint32_t b_lo = desc_lo(sbase + FwdSmem::STAGE0 + stage * STAGE_BYTES, b_lbo);
-              if (j == ns) {
-                umma_f16_lohi(tacc, ones_lo, a_hi, b_lo, b_hi, idesc, 1u);   // + bias
-              } else {
-                if (j == 0) { mbar_wait(&a_ready[t], a_phase); a_phase ^= 1; tc_fence_after(); }
-                const bool from_enc = (j >= first_enc) && (j < first_enc + es);
-                uint32_t a_lo;
-                if (from_enc) { a_lo = e_lo + ecol * A_K16; ecol += 2; } else { a_lo = h_lo + hcol * A_K16; hcol += 2; }
-                umma_f16_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, j > 0 ? 1u : 0u);
-                umma_f16_lohi(tacc, a_lo + A_K16, a_hi, b_lo + B_K16, b_hi, idesc, 1u);
-              }
-              umma_commit(&empty_bar[stage]);
-            } else {
-              mbar_arrive(&empty_bar[stage]);
-            }
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-          }
-          if (active) umma_commit(&d_ready[t]);
-        }
-      }
-    }
-  } else {
+  } else if (warp >= CH_WG_EPI0) {
     // =========================== epilogue warpgroups ===========================
-    const int t = (warp - EPI_WARP0) >> 2;            // tile slot handled by this warpgroup
+    const int g = (warp - CH_WG_EPI0) >> 2;           // accumulator region handled by this warpgroup
     const int row = 32 * (warp & 3) + lane;           // TMEM lane == tile row (a warp may only touch lanes 32*(warp%4)..)
     const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
-    uint8_t* Hb = smem + FwdSmem::H0 + t * H_BYTES;
-    uint8_t* Eb = smem + FwdSmem::ENC0 + t * ENC_BYTES;
-    const bool leader = ((warp - EPI_WARP0) & 3) == 0 && lane == 0;
-    const int bar_id = 1 + t;
+    const uint32_t tacc = tmem_base + tlane + (uint32_t)g * 128u;
     const float4* wa4 = reinterpret_cast<const float4*>(sparams + P.w_alpha_off);
-    const float* wr = sparams + P.w_rgb_off;
-    uint32_t d_phase = 0;
-    for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
-      const int64_t tile = 2 * st + t;
-      if (tile >= ntiles) continue;
+    const float4* wr4 = reinterpret_cast<const float4*>(sparams + P.w_rgb_off);
+    uint32_t d_phase = 0, aux_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t m = tile * TROWS + row;
-      const bool valid = m < M;
       uint8_t* rec = TRAIN ? stash + tile * (int64_t)P.rec_bytes : nullptr;
-      const uint32_t tacc = tmem_base + tlane + t * 256;
-      // ---- prologue: sample point + encodings
-      float vx = 0.f, vy = 0.f, vz = 0.f;
-      {
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-        if (valid) {
-          const int64_t r = m / S;
-          const float* rb = ray_batch + r * ray_stride;
-          const float zz = z[m];
-          x0 = __fadd_rn(rb[0], __fmul_rn(rb[3], zz));
-          x1 = __fadd_rn(rb[1], __fmul_rn(rb[4], zz));
-          x2 = __fadd_rn(rb[2], __fmul_rn(rb[5], zz));
-          vx = rb[8]; vy = rb[9]; vz = rb[10];
-        }
-        if (TRAIN) {                                   // previous tile's stash stores still read H/ENC
-          if (leader) bulk_wait_read_all();
-          named_bar_sync(bar_id, 128);
-        }
-        encode_row_to_smem<64>(Eb, row, x0, x1, x2, L_pts);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&a_ready[t]);
-      if (TRAIN) {
-        named_bar_sync(bar_id, 128);
-        if (leader) { bulk_s2g(rec + P.rec_encp, Eb, ENC_BYTES); bulk_commit(); }
-      }
       float alpha = 0.f;
-      for (int s = 0; s < P.nsteps; ++s) {
-        const FwdStep& S_ = P.steps[s];
-        mbar_wait(&d_ready[t], d_phase); d_phase ^= 1;
+      for (int s = 0; s < C.nsteps; ++s) {
+        const ChainStep& S_ = C.steps[s];
+        int half;
+        if (S_.nhalf == 2) half = g;
+        else if (S_.d0 == g) half = 0;
+        else continue;
+        mbar_wait(&B.d_ready[g], d_phase); d_phase ^= 1;
         tc_fence_after();
-        uint32_t ra[32], rb2[32];
-        tmem_ld32(tacc, ra);                           // overlaps with the stash bookkeeping below
-        if (TRAIN) {                                   // the H blob of the previous step is being stored
-          if (leader) bulk_wait_read_all();
-          named_bar_sync(bar_id, 128);
-        }
-        if (S_.epi == EPI_VIEWS) {
+        uint32_t ra[32], rb2[32], pw[16];
+        tmem_ld32(tacc, ra);
+        if (S_.epi != FE_VIEWS) {
+          const uint32_t a_dst = tmem_base + tlane + 256u + (uint32_t)S_.a_out * 128u + (uint32_t)half * 64u;
+          const int col0 = half * 128;
+          uint32_t mbits[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t (&r)[32] = (c & 1) ? rb2 : ra;
+            tmem_ld_wait();
+            if (c < 3) tmem_ld32(tacc + 32 * (c + 1), (c & 1) ? ra : rb2);
+            else chain_release_acc(B, g, lane);        // the whole region is in registers: next layer may overwrite it
+            if (TRAIN && S_.epi != FE_FEATURE) mbits[c] = sign_bits(r);
+            if (S_.epi == FE_TRUNK_LAST) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 w4 = wa4[((col0 + 32 * c) >> 2) + j4];
+                alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), w4.x, alpha);
+                alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f), w4.y, alpha);
+                alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), w4.z, alpha);
+                alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f), w4.w, alpha);
+              }
+            }
+            if (S_.epi == FE_FEATURE) pack_chunk<false>(r, pw);
+            else pack_chunk<true>(r, pw);
+            tmem_st16(a_dst + 16 * c, pw);
+            if (TRAIN) store_chunk_global(rec + S_.off0, col0 + 32 * c, row, pw);
+            if (c & 1) chain_publish(B, half * 2 + (c >> 1), lane);
+          }
+          if (TRAIN && S_.epi != FE_FEATURE)
+            *reinterpret_cast<uint4*>(rec + S_.off1 + row * 32 + half * 16) =
+                make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
+          if (S_.epi == FE_TRUNK_LAST && g == 0) {     // sigma partial sum of columns 0..127 -> warpgroup 1
+            s_alpha[row] = alpha;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&B.aux);
+          }
+        } else {
+          // views layer (always warpgroup 1): ReLU, rgb head, output
+          mbar_wait(&B.aux, aux_phase); aux_phase ^= 1;
+          alpha += s_alpha[row];
           float c0 = 0.f, c1 = 0.f, c2 = 0.f;
           uint32_t mbits[4];
 #pragma unroll
-          for (int cc = 0; cc < 128; cc += 64) {
+          for (int c = 0; c < 4; ++c) {
+            uint32_t (&r)[32] = (c & 1) ? rb2 : ra;
+            tmem_ld_wait();
+            if (c < 3) tmem_ld32(tacc + 32 * (c + 1), (c & 1) ? ra : rb2);
+            else chain_release_acc(B, g, lane);
 #pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-              uint32_t (&r)[32] = hb ? rb2 : ra;
-              const int c = cc + 32 * hb;
-              tmem_ld_wait();
-              if (c + 32 < 128) tmem_ld32(tacc + c + 32, hb ? ra : rb2);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float v = fmaxf(__uint_as_float(r[j]), 0.f);
-                c0 = fmaf(v, wr[c + j], c0);
-                c1 = fmaf(v, wr[128 + c + j], c1);
-                c2 = fmaf(v, wr[256 + c + j], c2);
-              }
-              if (TRAIN) {
-                mbits[c >> 5] = sign_bits(r);
-                store_chunk<true>(Hb, c, row, r);
-              }
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w0 = wr4[8 * c + j4], w1 = wr4[32 + 8 * c + j4], w2 = wr4[64 + 8 * c + j4];
+              const float v0 = fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), v1 = fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f);
+              const float v2 = fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), v3 = fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f);
+              c0 = fmaf(v0, w0.x, c0); c0 = fmaf(v1, w0.y, c0); c0 = fmaf(v2, w0.z, c0); c0 = fmaf(v3, w0.w, c0);
+              c1 = fmaf(v0, w1.x, c1); c1 = fmaf(v1, w1.y, c1); c1 = fmaf(v2, w1.z, c1); c1 = fmaf(v3, w1.w, c1);
+              c2 = fmaf(v0, w2.x, c2); c2 = fmaf(v1, w2.y, c2); c2 = fmaf(v2, w2.z, c2); c2 = fmaf(v3, w2.w, c2);
+            }
+            if (TRAIN) {
+              mbits[c] = sign_bits(r);
+              pack_chunk<true>(r, pw);
+              store_chunk_global(rec + S_.off0, 32 * c, row, pw);
             }
           }
-          if (valid) {
+          if (m < M) {
             const float* bh = sparams + P.b_head_off;
-            float4 o = make_float4(c0 + bh[1], c1 + bh[2], c2 + bh[3], alpha + bh[0]);
-            reinterpret_cast<float4*>(out)[m] = o;
+            reinterpret_cast<float4*>(out)[m] = make_float4(c0 + bh[1], c1 + bh[2], c2 + bh[3], alpha + bh[0]);
           }
-          if (TRAIN) {
-            *reinterpret_cast<uint4*>(rec + P.rec_maskv + row * 16) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-            fence_proxy_async();
-            named_bar_sync(bar_id, 128);
-            if (leader) { bulk_s2g(rec + P.rec_hv, Hb, HV_BYTES); bulk_commit(); }
-          }
-          tc_fence_before();   // orders our TMEM reads before the next tile's a_ready arrive
-        } else {
-          uint32_t mbits[8];
-#pragma unroll
-          for (int cc = 0; cc < TW; cc += 64) {
-#pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-              uint32_t (&r)[32] = hb ? rb2 : ra;
-              const int c = cc + 32 * hb;
-              tmem_ld_wait();
-              if (c + 32 < TW) tmem_ld32(tacc + c + 32, hb ? ra : rb2);
-              if (TRAIN && S_.epi == EPI_TRUNK) mbits[c >> 5] = sign_bits(r);
-              if (S_.last_trunk) {
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 w4 = wa4[(c >> 2) + j4];
-                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), w4.x, alpha);
-                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f), w4.y, alpha);
-                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), w4.z, alpha);
-                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f), w4.w, alpha);
-                }
-              }
-              if (S_.epi == EPI_TRUNK) store_chunk<true>(Hb, c, row, r);
-              else store_chunk<false>(Hb, c, row, r);
-            }
-          }
-          if (S_.epi == EPI_FEATURE)   // the encoding buffer is dead after the trunk: reuse it for gamma(viewdirs)
-            encode_row_to_smem<32>(Eb, row, vx, vy, vz, L_views);
-          if (TRAIN && S_.epi == EPI_TRUNK) {
-            uint4* mp = reinterpret_cast<uint4*>(rec + P.rec_mask + (s * TROWS + row) * 32);
-            mp[0] = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-            mp[1] = make_uint4(mbits[4], mbits[5], mbits[6], mbits[7]);
-          }
-          fence_proxy_async();
-          tc_fence_before();
-          mbar_arrive(&a_ready[t]);
-          if (TRAIN) {
-            named_bar_sync(bar_id, 128);
-            if (leader) {
-              bulk_s2g(rec + P.rec_h0 + S_.stash_slot * H_BYTES, Hb, H_BYTES);
-              if (S_.epi == EPI_FEATURE) bulk_s2g(rec + P.rec_encv, Eb, ENCV_BYTES);
-              bulk_commit();
-            }
-          }
+          if (TRAIN)
+            *reinterpret_cast<uint4*>(rec + S_.off1 + row * 16) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
         }
       }
     }
-    if (TRAIN && leader) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-static size_t fwd_smem_bytes(const FwdPlan& P) { return (size_t)FwdSmem::PARAMS + (size_t)P.nparam_floats * 4; }
+static size_t fwd_smem_bytes(const FwdPlan& P) { return (size_t)ChSmem::PARAMS + (size_t)P.nparam_floats * 4; }
 
 // head weights gathered into one contiguous float block: w_alpha[256] | w_rgb[3][128] | b_alpha, b_rgb[3]
 __global__ void gather_fwd_params_kernel(const float* __restrict__ params, float* __restrict__ dst, MlpLayout L,
@@ -442,7 +378,9 @@ size_t lush_mlp_tc_workspace_bytes(const MlpLayout& L, int64_t R, int S, int tra
   if (training) return lush_mlp_tc_bwd_workspace_bytes(L, R, S);
   FwdPlan P;
   make_fwd_plan(L, P);
-  return (size_t)((P.wstream_bytes + 255) / 256) * 256 + (size_t)P.nparam_floats * 4 + 256;
+  ChainPlan C;
+  make_fwd_chain(L, P, C);
+  return (size_t)((C.stream_bytes + 255) / 256) * 256 + (size_t)P.nparam_floats * 4 + 256;
 }
 
 // biases + head weights gathered into one float block (also used by the backward kernels)
@@ -466,31 +404,35 @@ int lush_mlp_tc_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
   }
   LUSH_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)stash & 15) == 0,
                "mlp_fwd(tc): unaligned buffers");
+  ChainPlan C;
+  make_fwd_chain(L, P, C);
   __half* wstream = reinterpret_cast<__half*>(workspace);
-  float* gparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((P.wstream_bytes + 255) / 256) * 256);
+  float* gparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((C.stream_bytes + 255) / 256) * 256);
   PackPlan K;
-  make_pack_plan(L, P, K);
+  make_pack_plan(L, C, K);
   pack_fwd_weights_kernel<<<dim3(64, K.njobs), 256, 0, st>>>(params, wstream, K);
   LUSH_LAUNCH_CHECK("pack_fwd_weights");
   int rc = lush_tc_gather_head_params(L, params, gparams, st);
   if (rc) return rc;
   const int64_t M = R * S;
-  const int64_t ntiles = (M + TROWS - 1) / TROWS, nsuper = (ntiles + 1) / 2;
+  const int64_t ntiles = (M + TROWS - 1) / TROWS;
   const size_t smem = fwd_smem_bytes(P);
-  LUSH_REQUIRE(smem + 256 <= 227 * 1024, "mlp_fwd(tc): shared memory budget exceeded (%zu)", smem);
-  int grid = (int)(nsuper < kNumSMs ? nsuper : kNumSMs);
+  LUSH_REQUIRE(smem + 2048 <= 227 * 1024, "mlp_fwd(tc): shared memory budget exceeded (%zu)", smem);
+  int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   if (stash != nullptr) {
     rc = check_cuda(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem), "mlp_fwd(tc): smem attr");
     if (rc) return rc;
-    mlp_tc_fwd_kernel<true><<<grid, FWD_THREADS, smem, st>>>(wstream, gparams, ray_batch, ray_stride, z, out,
-                                                            (uint8_t*)stash, M, S, desc->L_pts, desc->L_views, P);
+    mlp_tc_fwd_kernel<true><<<grid, CH_THREADS, smem, st>>>((const uint8_t*)wstream, gparams, ray_batch, ray_stride,
+                                                           z, out, (uint8_t*)stash, M, S, desc->L_pts,
+                                                           desc->L_views, C, P);
   } else {
     rc = check_cuda(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem), "mlp_fwd(tc): smem attr");
     if (rc) return rc;
-    mlp_tc_fwd_kernel<false><<<grid, FWD_THREADS, smem, st>>>(wstream, gparams, ray_batch, ray_stride, z, out,
-                                                             nullptr, M, S, desc->L_pts, desc->L_views, P);
+    mlp_tc_fwd_kernel<false><<<grid, CH_THREADS, smem, st>>>((const uint8_t*)wstream, gparams, ray_batch, ray_stride,
+                                                            z, out, nullptr, M, S, desc->L_pts, desc->L_views, C,
+                                                            P);
   }
   LUSH_LAUNCH_CHECK("mlp_tc_fwd");
   return 0;

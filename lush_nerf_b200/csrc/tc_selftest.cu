@@ -6,7 +6,8 @@
 namespace lush {
 using namespace tc;
 
-// a_mode / b_mode: 0 = K-major view, 1 = MN-major view of the blob
+// a_mode / b_mode: 0 = K-major view, 1 = MN-major view of the blob; a_mode = 2: A is first moved to TENSOR MEMORY
+// (tcgen05.st, two fp16 per 32-bit column) and the MMA reads it from there (the fused MLP's activation path)
 // K-major A: blob rows = 128 (M), cols = K.   MN-major A: blob rows = K, cols = 128 (M).
 // K-major B: blob rows = N, cols = K.         MN-major B: blob rows = K, cols = N.
 __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half* __restrict__ a_blob,
@@ -28,13 +29,37 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half* __restri
     mbar_init(&bar, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  if (tid == 0) {
+  if (a_mode == 2) {   // row tid of A: K fp16 -> K/2 columns of lane tid, starting at column 256
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      uint32_t pk[16];
+      for (int g = 0; g < 4; ++g) {
+        const uint4 q = *reinterpret_cast<const uint4*>(sa + blob_off(128, tid, k0 + 8 * g));
+        pk[4 * g] = q.x; pk[4 * g + 1] = q.y; pk[4 * g + 2] = q.z; pk[4 * g + 3] = q.w;
+      }
+      tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + 256 + k0 / 2, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (tid == 0 && a_mode == 2) {
+    const uint32_t idesc = make_idesc_f16(128, N, 0, b_mode);
+    const uint32_t b_rows = b_mode == 0 ? (uint32_t)N : (uint32_t)K;
+    const uint32_t b_lbo = b_mode == 0 ? b_rows * 16u : 128u, b_sbo = b_mode == 0 ? 128u : b_rows * 16u;
+    const uint32_t b_step = b_mode == 0 ? 2u * b_rows * 16u : 256u;
+    for (int k = 0; k < K / 16; ++k) {
+      uint64_t bd = make_smem_desc(smem_u32(sb) + k * b_step, b_lbo, b_sbo);
+      umma_f16_ts(tmem_base, tmem_base + 256 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar);
+  } else if (tid == 0) {
     const uint32_t idesc = make_idesc_f16(128, N, a_mode, b_mode);
     // per K=16 step: K-major advances two 8-column groups (2*rows*16 B); MN-major advances 16 rows (256 B)
     const uint32_t a_rows = a_mode == 0 ? 128u : (uint32_t)K;
@@ -66,7 +91,7 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half* __restri
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace lush

@@ -19,7 +19,7 @@ def to_blob(mat: torch.Tensor) -> torch.Tensor:
 def run(A, B, a_mode, b_mode, swap=0):
     """A [128,K], B [N,K] fp16 (logical).  MN-major views store the transposed matrix in the blob."""
     N, K = B.shape
-    a_blob = to_blob(A if a_mode == 0 else A.t().contiguous()).cuda()
+    a_blob = to_blob(A if a_mode != 1 else A.t().contiguous()).cuda()
     b_blob = to_blob(B if b_mode == 0 else B.t().contiguous()).cuda()
     out = torch.full((128, N), float("nan"), device="cuda")
     rc = _lib.lib().lush_tc_selftest(ctypes.c_void_p(a_blob.data_ptr()), ctypes.c_void_p(b_blob.data_ptr()),
@@ -42,3 +42,16 @@ def test_umma_descriptor_conventions(a_mode, b_mode, N, K):
         alt = run(A, B, a_mode, b_mode, swap=1)
         err_alt = (alt - ref).abs().max().item()
         pytest.fail(f"UMMA result wrong: max err {err:.3e} (with LBO/SBO swapped: {err_alt:.3e})")
+
+
+@pytest.mark.parametrize("b_mode", [0, 1])
+@pytest.mark.parametrize("N,K", [(256, 64), (128, 32), (128, 256), (64, 256), (16, 32)])
+def test_umma_a_operand_from_tensor_memory(b_mode, N, K):
+    """A written to TMEM with tcgen05.st (two fp16 per column, lane = row) and consumed by tcgen05.mma [d],[a],b."""
+    g = torch.Generator().manual_seed(N * 11 + K)
+    A = (torch.randn(128, K, generator=g) * 0.5).half()
+    B = (torch.randn(N, K, generator=g) * 0.5).half()
+    ref = A.float() @ B.float().t()
+    out = run(A, B, 2, b_mode)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3, f"TS-mode UMMA wrong: max err {err:.3e}"

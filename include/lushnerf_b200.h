@@ -182,6 +182,14 @@ int lush_blend_tonemap_bwd(const float* rgb, const float* ccw, const float* nois
 int lush_tc_selftest(const void* a_blob, const void* b_blob, float* d_out, int N, int K, int a_mode,
                      int b_mode, int swap_lbo_sbo, void* stream);
 
+/* Tensor-pipe micro-benchmark (tools/bench_umma.py; not on the product path): `iters` back-to-back
+ * tcgen05.mma M=128 K=16 from one thread; out_cycles[0] = issue cycles, out_cycles[1] = cycles to completion.
+ * flags (per block of 8 MMAs): 1 = tcgen05.commit, 2 = tcgen05.fence::after_thread_sync, 4 = mbarrier wait. */
+int lush_tc_microbench(long long* out_cycles, int N, int nacc, int a_tmem, int iters, int flags, void* stream);
+/* Debug: copy the forward chain kernel's timeline trace (LUSH_CHAIN_DEBUG=2; clock64 stamps of CTA 0, third tile,
+ * slot = step*16 + event) to host memory. */
+int lush_debug_read_chain_trace(long long* host_out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "lush_blend_tonemap_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "lush_blend_tonemap_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "lush_tc_selftest": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "lush_tc_microbench": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "lush_debug_read_chain_trace": (c_int, [_P, c_int]),
 }
 
 _lib = None

@@ -9,19 +9,26 @@
 //     operands in shared memory;
 //   * shared memory is almost entirely a ring (5 x 32 KB) of weight blocks [128 out x 128 K] streamed with
 //     bulk async copies (TMA engine) in exactly the order the MMAs consume them.
-// Each layer is issued as two N=128 halves.  While the tensor core works on half 1 of layer s, epilogue
-// warpgroup 0 drains half 0 (tcgen05.ld -> activation -> fp16 -> tcgen05.st) and publishes the next layer's
-// A operand 64 columns at a time (one mbarrier each), so layer s+1 starts as soon as its first K-slices
-// exist: the tensor pipe does not wait for a whole-layer hand-off.
+// Each layer is issued as two N=128 halves, strictly in order (s,h0) (s,h1) (s+1,h0) ...  While the tensor core
+// works on half 1 of layer s, ALL eight epilogue warps drain half 0 (tcgen05.ld -> bias/activation -> fp16 ->
+// tcgen05.st; warpgroup g takes 64 of the 128 columns) and publish it as the first 128 K-values of the next
+// layer's A operand (one mbarrier per half), so layer s+1 starts on them while half 1 is being drained: the
+// tensor pipe never waits for a whole-layer hand-off.
 //
 // Warp roles (512 threads, 1 CTA per SM, persistent over tiles):
-//   warp 0        weight producer (one lane)
-//   warp 1        MMA issuer (converged warp, elected lane issues), TMEM allocation
-//   warps 4-7     epilogue warpgroup 0  (accumulator region 0)
-//   warps 8-11    epilogue warpgroup 1  (accumulator region 1)
-//   warps 12-15   prologue warpgroup: builds the NEXT tile's shared-memory operands (positional encodings /
+//   warps 0-3     prologue warpgroup: builds the NEXT tile's shared-memory operands (positional encodings /
 //                 head-gradient tile) while the current tile is in flight (double-buffered)
+//   warps 4-7     epilogue warpgroup 0  (columns  0..63  of every output half)
+//   warps 8-11    epilogue warpgroup 1  (columns 64..127 of every output half)
+//   warp 12       weight producer (one lane)
+//   warps 14, 15  MMA issuers (converged warps, one elected lane issues): warp 1+r issues everything that
+//                 targets accumulator region r (single-thread issue costs ~80 cycles per MMA, more than the
+//                 64 cycles an N=128 MMA occupies the tensor pipe, so the work is split); a token barrier keeps
+//                 the pipe order (s,h0) before (s,h1).  Warp 14 also owns the TMEM allocation.
+// The SM's warp arbiter favours the highest warp id among eligible warps: the latency-critical single-thread
+// issuers sit at the top, the ALU-heavy but latency-tolerant encoder warps at the bottom.
 #pragma once
+#include <stdlib.h>
 #include "mlp_tc.cuh"
 
 namespace lush {
@@ -30,8 +37,10 @@ constexpr int CH_THREADS = 512;
 constexpr int CH_NSTAGE = 5;
 constexpr int CH_STAGE_BYTES = 128 * 128 * 2;  // 32 KB: one [128 x 128] fp16 weight block (K = 128)
 constexpr int CH_MAX_STEPS = kMaxDepth + 6;
+constexpr int CH_WG_PRO = 0;                   // first warp of the prologue warpgroup
 constexpr int CH_WG_EPI0 = 4;                  // first warp of epilogue warpgroup 0
-constexpr int CH_WG_PRO = 12;                  // first warp of the prologue warpgroup
+constexpr int CH_WARP_PRODUCER = 12;
+constexpr int CH_WARP_MMA0 = 14;               // issuer of accumulator region 0 (region 1: CH_WARP_MMA0 + 1)
 constexpr int CH_X16_BYTES = TROWS * 16 * 2;   // [128 x 16] fp16 tile
 
 struct ChSmem {
@@ -65,6 +74,7 @@ struct ChainStep {
 
 struct ChainPlan {
   int nsteps;
+  int debug;              // experiments only (LUSH_CHAIN_DEBUG): bit 0 = do not stream weights (results are garbage)
   int64_t stream_bytes;   // weight stream per tile
   ChainStep steps[CH_MAX_STEPS];
 };
@@ -76,28 +86,43 @@ __host__ __device__ inline int chain_half_bytes(const ChainStep& s) {
   return chain_small_bytes(s) + s.NH * 2 * KS * s.h_slices;
 }
 static inline void chain_finish_plan(ChainPlan& P) {
+  const char* dbg = getenv("LUSH_CHAIN_DEBUG");
+  P.debug = dbg ? atoi(dbg) : 0;
   int64_t b = 0;
   for (int s = 0; s < P.nsteps; ++s) b += (int64_t)P.steps[s].nhalf * chain_half_bytes(P.steps[s]);
   P.stream_bytes = b;
 }
 
+// ---- optional timeline trace (LUSH_CHAIN_DEBUG bit 1): CTA 0 records clock64() of its third tile's events
+//   slot = step*16 + {0,1: issue of half 0 start/end; 2,3: half 1; 4 + 4*half + {0: d_ready seen, 1: accumulator
+//   released, 2: published} for epilogue warpgroup 0; 12..: warpgroup 1 half 0 d_ready seen / published}
+static __device__ long long g_chain_trace[CH_MAX_STEPS * 16];   // one copy per translation unit
+__device__ __forceinline__ void chain_trace(const ChainPlan& P, int64_t it, int step, int ev) {
+  if ((P.debug & 2) && blockIdx.x == 0 && it == 2 && (threadIdx.x & 31) == 0) g_chain_trace[step * 16 + ev] = clock64();
+}
+
 struct ChainBars {
   uint64_t full[CH_NSTAGE], empty[CH_NSTAGE];
-  uint64_t a_ready[4];          // 64-column group j of the activation buffer being written is complete (4 warps)
+  uint64_t a_ready[2][2][2];    // [issuer][buf][j]: K-values [128j, 128j+128) of activation buffer `buf` are complete
+                                // (8 warps).  One set per issuer (each tracks its own parity) and per buffer: a
+                                // barrier then completes again only two steps later, which transitively requires
+                                // both issuers to have observed the previous completion (no parity aliasing)
+  uint64_t h0_issued;           // issuer 0 has issued half 0 of the current two-half step (pipe order token)
   uint64_t d_ready[2];          // accumulator region r complete (MMA commit)
-  uint64_t d_free[2];           // accumulator region r drained by its epilogue warpgroup (4 warps)
+  uint64_t d_free[2];           // accumulator region r is in the epilogue warps' registers (8 warps)
   uint64_t pro_ready[2];        // prologue operands of tile parity b are in shared memory (4 warps)
   uint64_t pro_free[2];         // ... and no longer read by any MMA (commit)
-  uint64_t aux;                 // kernel-specific (forward: sigma partial sums of warpgroup 0)
+  uint64_t aux;                 // kernel-specific (forward: head partial sums of warpgroup 0, 4 warps)
 };
 
 __device__ __forceinline__ void chain_init_bars(ChainBars& B) {
   for (int s = 0; s < CH_NSTAGE; ++s) { mbar_init(&B.full[s], 1); mbar_init(&B.empty[s], 1); }
-  for (int j = 0; j < 4; ++j) mbar_init(&B.a_ready[j], 4);
   for (int r = 0; r < 2; ++r) {
-    mbar_init(&B.d_ready[r], 1); mbar_init(&B.d_free[r], 4);
-    mbar_init(&B.pro_ready[r], 4); mbar_init(&B.pro_free[r], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&B.a_ready[i][r][0], 8); mbar_init(&B.a_ready[i][r][1], 8); }
+    mbar_init(&B.d_ready[r], 1); mbar_init(&B.d_free[r], 8);
+    mbar_init(&B.pro_ready[r], 4); mbar_init(&B.pro_free[r], 2);
   }
+  mbar_init(&B.h0_issued, 1);
   mbar_init(&B.aux, 4);
   fence_barrier_init();
 }
@@ -116,8 +141,11 @@ __device__ __forceinline__ void chain_producer(ChainBars& B, uint8_t* smem, cons
         for (int j = (small ? -1 : 0); j < nbig; ++j) {
           const uint32_t bytes = j < 0 ? small : big;
           mbar_wait(&B.empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&B.full[stage], bytes);
-          bulk_g2s(smem + ChSmem::STAGE0 + stage * CH_STAGE_BYTES, src, bytes, &B.full[stage]);
+          if (P.debug & 1) { mbar_arrive(&B.full[stage]); }
+          else {
+            mbar_arrive_expect_tx(&B.full[stage], bytes);
+            bulk_g2s(smem + ChSmem::STAGE0 + stage * CH_STAGE_BYTES, src, bytes, &B.full[stage]);
+          }
           src += bytes;
           if (++stage == CH_NSTAGE) { stage = 0; phase ^= 1; }
         }
@@ -188,18 +216,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// ---- warp 1 (all 32 lanes, converged): issue every MMA of every tile
+// ---- warps 1 and 2 (all 32 lanes, converged): issuer `my` issues every MMA that targets accumulator region
+// `my`.  Both walk the same block sequence of the weight ring and skip each other's blocks.
 __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, uint32_t tmem_base,
-                                                 const ChainPlan& P, int64_t ntiles, int lane) {
-  int stage = 0; uint32_t phase = 0;
-  uint32_t a_phase = 0;                 // bit j: parity to wait for on a_ready[j]
-  uint32_t dfree_phase = 0, d_used = 0; // bit r
+                                                 const ChainPlan& P, int64_t ntiles, const uint32_t my) {
+  uint32_t stage = 0, phase = 0;
+  uint32_t a_phase = 0, dfree_phase = 0, d_used = 0, tok_phase = 0;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t hi128 = desc_hi(128u);
+  const uint32_t tacc = tmem_base + my * 128u;
   constexpr uint32_t A_K16 = (2u * TROWS * 16u) >> 4;   // start-address units per 16 columns of a 128-row blob
   int64_t it = 0;
-  // the full barrier of the next stage is polled one block ahead so its latency hides behind the MMA issue
-  bool full_ok = mbar_test_wait(&B.full[0], 0);
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int b = (int)(it & 1);
     mbar_wait(&B.pro_ready[b], (uint32_t)((it >> 1) & 1));
@@ -213,72 +240,78 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
       const uint32_t B_K16 = (2u * b_lbo) >> 4;
       const uint32_t a_tmem = tmem_base + 256u + (uint32_t)S.a_in * 128u;
       const uint32_t e_lo = S.enc_src ? encv_lo : enc_lo;
-      const bool has_small = S.pre16 || S.enc_slices;
-      const int nbig = S.h_slices >> 2;
+      const uint32_t has_small = (S.pre16 || S.enc_slices) ? 1u : 0u;
+      const uint32_t nbig = (uint32_t)S.h_slices >> 2;
+      const uint32_t a_todo = S.wait_a ? nbig : 0u;   // 128-K groups of the new A buffer this issuer must observe
+      uint32_t a_seen = 0;
       for (int h = 0; h < S.nhalf; ++h) {
         const uint32_t reg = (h == 0) ? (uint32_t)S.d0 : 1u;
-        if ((d_used >> reg) & 1u) {
-          mbar_wait(&B.d_free[reg], (dfree_phase >> reg) & 1u); dfree_phase ^= (1u << reg);
+        if (reg != my) {                       // the other issuer's blocks
+          stage += has_small + nbig;
+          if (stage >= CH_NSTAGE) { stage -= CH_NSTAGE; phase ^= 1u; }
+          continue;
         }
-        d_used |= (1u << reg);
-        const uint32_t tacc = tmem_base + reg * 128u;
+        if (d_used) { mbar_wait(&B.d_free[my], dfree_phase); dfree_phase ^= 1u; }
+        d_used = 1u;
+        if (h == 1 && !(P.debug & 16)) { mbar_wait(&B.h0_issued, tok_phase); tok_phase ^= 1u; }   // keep the pipe order (s,h0) (s,h1)
+        chain_trace(P, it, s, 2 * h);
         uint32_t acc = 0;
-        for (int j = (has_small ? -1 : 0); j < nbig; ++j) {
-          if (!full_ok) mbar_wait(&B.full[stage], phase);
-          const int nstage = (stage + 1 == CH_NSTAGE) ? 0 : stage + 1;
-          const uint32_t nphase = (stage + 1 == CH_NSTAGE) ? (phase ^ 1u) : phase;
-          full_ok = mbar_test_wait(&B.full[nstage], nphase);
-          uint32_t b_lo = desc_lo(sbase + ChSmem::STAGE0 + stage * CH_STAGE_BYTES, b_lbo);
-          if (j < 0) {
-            tc_fence_after();
-            if (elect_one()) {
-              uint32_t acc1 = acc;
-              if (S.pre16) {
-                mma_ss<1>(tacc, x16_lo, b_lo, hi128, A_K16, B_K16, idesc, acc1); acc1 = 1;
-                b_lo += B_K16;
-              }
-              if (S.enc_slices == 2) mma_ss<4>(tacc, e_lo, b_lo, hi128, A_K16, B_K16, idesc, acc1);
-              else if (S.enc_slices == 1) mma_ss<2>(tacc, e_lo, b_lo, hi128, A_K16, B_K16, idesc, acc1);
-              umma_commit(&B.empty[stage]);
-            }
-            __syncwarp();
-            acc = 1;
-          } else {
-            const bool wa = (h == 0) && S.wait_a;
-            if (wa) { mbar_wait(&B.a_ready[2 * j], (a_phase >> (2 * j)) & 1u); a_phase ^= (1u << (2 * j)); }
-            tc_fence_after();
-            if (elect_one()) mma_ts_k64(tacc, a_tmem + (uint32_t)j * 64u, b_lo, hi128, B_K16, idesc, acc);
-            __syncwarp();
-            acc = 1;
-            if (wa) {
-              mbar_wait(&B.a_ready[2 * j + 1], (a_phase >> (2 * j + 1)) & 1u); a_phase ^= (1u << (2 * j + 1));
-              tc_fence_after();
-            }
-            if (elect_one()) {
-              mma_ts_k64(tacc, a_tmem + (uint32_t)j * 64u + 32u, b_lo + 4u * B_K16, hi128, B_K16, idesc, 1u);
-              umma_commit(&B.empty[stage]);
-            }
-            __syncwarp();
+        if (has_small) {
+          mbar_wait(&B.full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            uint32_t b_lo = desc_lo(sbase + ChSmem::STAGE0 + stage * CH_STAGE_BYTES, b_lbo);
+            uint32_t acc1 = 0;
+            if (S.pre16) { mma_ss<1>(tacc, x16_lo, b_lo, hi128, A_K16, B_K16, idesc, acc1); acc1 = 1; b_lo += B_K16; }
+            if (S.enc_slices == 2) mma_ss<4>(tacc, e_lo, b_lo, hi128, A_K16, B_K16, idesc, acc1);
+            else if (S.enc_slices == 1) mma_ss<2>(tacc, e_lo, b_lo, hi128, A_K16, B_K16, idesc, acc1);
+            umma_commit(&B.empty[stage]);
           }
-          stage = nstage; phase = nphase;
+          acc = 1;
+          if (++stage == CH_NSTAGE) { stage = 0; phase ^= 1u; }
         }
-        if (elect_one()) umma_commit(&B.d_ready[reg]);
-        __syncwarp();
+        for (uint32_t j = 0; j < nbig; ++j) {
+          mbar_wait(&B.full[stage], phase);
+          if (a_seen < a_todo) {
+            const uint32_t k = 2u * (uint32_t)S.a_in + j;
+            mbar_wait(&B.a_ready[my][S.a_in][j], (a_phase >> k) & 1u); a_phase ^= (1u << k); a_seen = j + 1;
+          }
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t b_lo = desc_lo(sbase + ChSmem::STAGE0 + stage * CH_STAGE_BYTES, b_lbo);
+            mma_ts_k64(tacc, a_tmem + j * 64u, b_lo, hi128, B_K16, idesc, acc);
+            mma_ts_k64(tacc, a_tmem + j * 64u + 32u, b_lo + 4u * B_K16, hi128, B_K16, idesc, 1u);
+            umma_commit(&B.empty[stage]);
+          }
+          acc = 1;
+          if (j == 0) chain_trace(P, it, s, 14 + h);
+          if (++stage == CH_NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+        if (elect_one()) {
+          umma_commit(&B.d_ready[my]);
+          if (h == 0 && S.nhalf == 2) mbar_arrive(&B.h0_issued);
+        }
+        chain_trace(P, it, s, 2 * h + 1);
+      }
+      // groups this issuer did not need (it issued nothing in this step): observe them anyway so that the
+      // parity bookkeeping of a_ready[my][*] never skips a phase
+      for (; a_seen < a_todo; ++a_seen) {
+        const uint32_t k = 2u * (uint32_t)S.a_in + a_seen;
+        mbar_wait(&B.a_ready[my][S.a_in][a_seen], (a_phase >> k) & 1u); a_phase ^= (1u << k);
       }
     }
-    if (elect_one()) umma_commit(&B.pro_free[b]);   // every MMA reading this tile's shared-memory operands is complete
-    __syncwarp();
+    if (elect_one()) umma_commit(&B.pro_free[b]);   // my MMAs reading this tile's shared-memory operands are complete
   }
 }
 
-// epilogue side of the hand-off: this warp's tcgen05.st of 64-column group j are complete -> publish
-__device__ __forceinline__ void chain_publish(ChainBars& B, int j, int lane) {
+// epilogue side of the hand-off: this warp's tcgen05.st into K-values [128j, 128j+128) of buffer `buf` are complete
+__device__ __forceinline__ void chain_publish(ChainBars& B, int buf, int j, int lane) {
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(&B.a_ready[j]);
+  if (lane == 0) { mbar_arrive(&B.a_ready[0][buf][j]); mbar_arrive(&B.a_ready[1][buf][j]); }
 }
-// all accumulator columns of region r are in registers
+// this warp's share of accumulator region r is in registers
 __device__ __forceinline__ void chain_release_acc(ChainBars& B, int r, int lane) {
   tc_fence_before();
   __syncwarp();

@@ -4,8 +4,8 @@
 // models/lushnerf.py:234-266 (mlpforward) for W = 256 networks.
 //
 // The kernel is one instance of the chain skeleton in mlp_chain.cuh (read that header first):
-//   steps 0..D-1   trunk layers (bias via a ones-column K=16 slice, gamma(x) via SS-mode slices, hidden state
-//                  via TS-mode slices straight from tensor memory), ReLU fused into the fp16 conversion
+//   steps 0..D-1   trunk layers (gamma(x) via SS-mode slices, hidden state via TS-mode slices straight from
+//                  tensor memory); fp32 bias add and ReLU fused into the fp16 conversion of the epilogue
 //   step D         feature_linear (no activation)
 //   step D+1       views_linears[0] on [feature | gamma(viewdirs)], N = 128, accumulator region 1
 // The sigma head (256->1) and rgb head (128->3) are fp32 register dot products over the accumulators in the
@@ -25,7 +25,7 @@ static void make_fwd_chain(const MlpLayout& L, const FwdPlan& P, ChainPlan& C) {
   int n = 0;
   for (int i = 0; i < L.D; ++i) {
     ChainStep& s = C.steps[n];
-    s.nhalf = 2; s.d0 = 0; s.NH = 128; s.pre16 = 1; s.enc_src = 0;
+    s.nhalf = 2; s.d0 = 0; s.NH = 128; s.pre16 = 0; s.enc_src = 0;
     const bool enc = (i == 0) || (L.skip >= 0 && i == L.skip + 1);
     s.enc_slices = enc ? 2 : 0;
     s.h_slices = (i == 0) ? 0 : TW / KS;
@@ -37,12 +37,12 @@ static void make_fwd_chain(const MlpLayout& L, const FwdPlan& P, ChainPlan& C) {
     ++n;
   }
   { ChainStep& s = C.steps[n];
-    s.nhalf = 2; s.d0 = 0; s.NH = 128; s.pre16 = 1; s.enc_src = 0; s.enc_slices = 0; s.h_slices = TW / KS;
+    s.nhalf = 2; s.d0 = 0; s.NH = 128; s.pre16 = 0; s.enc_src = 0; s.enc_slices = 0; s.h_slices = TW / KS;
     s.a_in = (int8_t)(n & 1); s.wait_a = 1; s.a_out = (int8_t)((n + 1) & 1);
     s.epi = FE_FEATURE; s.p0 = 0; s.p1 = 0; s.off0 = P.rec_feat; s.off1 = 0;
     ++n; }
   { ChainStep& s = C.steps[n];
-    s.nhalf = 1; s.d0 = 1; s.NH = 128; s.pre16 = 1; s.enc_src = 1; s.enc_slices = 1; s.h_slices = TW / KS;
+    s.nhalf = 1; s.d0 = 1; s.NH = 128; s.pre16 = 0; s.enc_src = 1; s.enc_slices = 1; s.h_slices = TW / KS;
     s.a_in = (int8_t)(n & 1); s.wait_a = 1; s.a_out = -1;
     s.epi = FE_VIEWS; s.p0 = 0; s.p1 = 0; s.off0 = P.rec_hv; s.off1 = P.rec_maskv;
     ++n; }
@@ -187,30 +187,26 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ ChainBars B;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_alpha[TROWS];
+  __shared__ float4 s_part[TROWS];   // warpgroup 0's partial (rgb, sigma) head sums of the current tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + TROWS - 1) / TROWS;
-  float* sparams = reinterpret_cast<float*>(smem + ChSmem::PARAMS);
+  float* sparams = reinterpret_cast<float*>(smem + ChSmem::X160);   // the forward has no X16 operand: params live there
 
   for (int i = tid; i < P.nparam_floats; i += CH_THREADS) sparams[i] = params_smem_src[i];
-  // ones operand (both buffers): row r -> [1, 0 x 7 | 0 x 8]: the K=16 slice that adds the bias inside the MMA
-  for (int i = tid; i < 2 * CH_X16_BYTES / 16; i += CH_THREADS)
-    *reinterpret_cast<uint4*>(smem + ChSmem::X160 + i * 16) =
-        ((i % (CH_X16_BYTES / 16)) < TROWS) ? make_uint4(0x3C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) chain_init_bars(B);
-  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  if (warp == CH_WARP_MMA0) tmem_alloc(&tmem_base_s, 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
+  if (warp == CH_WARP_PRODUCER) {
     if (lane == 0) chain_producer(B, smem, wstream, C, ntiles);
-  } else if (warp == 1) {
-    chain_mma_issuer(B, smem, tmem_base, C, ntiles, lane);
-  } else if (warp >= CH_WG_PRO) {
+  } else if (warp >= CH_WARP_MMA0) {
+    chain_mma_issuer(B, smem, tmem_base, C, ntiles, (uint32_t)(warp - CH_WARP_MMA0));
+  } else if (warp < CH_WG_EPI0) {
     // =========================== prologue warpgroup: sample points + encodings of the NEXT tile ===========
     const int row = tid - CH_WG_PRO * 32;
     int64_t it = 0;
@@ -229,114 +225,137 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         vx = rb[8]; vy = rb[9]; vz = rb[10];
       }
       uint8_t* rec = TRAIN ? stash + tile * (int64_t)P.rec_bytes : nullptr;
+      if (!(C.debug & 8) || it < 2) {
       encode_row<64>(smem + ChSmem::ENC0 + b * ENC_BYTES, TRAIN ? rec + P.rec_encp : nullptr, row, x0, x1, x2, L_pts);
       encode_row<32>(smem + ChSmem::ENCV0 + b * ENCV_BYTES, TRAIN ? rec + P.rec_encv : nullptr, row, vx, vy, vz,
                      L_views);
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.pro_ready[b]);
     }
-  } else if (warp >= CH_WG_EPI0) {
+  } else if (warp < CH_WARP_PRODUCER) {
     // =========================== epilogue warpgroups ===========================
-    const int g = (warp - CH_WG_EPI0) >> 2;           // accumulator region handled by this warpgroup
+    // Both warpgroups drain every output half: warpgroup g owns columns [64g, 64g+64) of the half (two chunks of
+    // 32), loads both chunks at once, releases the accumulator, and publishes its 64 K-values of the next layer.
+    const int g = (warp - CH_WG_EPI0) >> 2;
     const int row = 32 * (warp & 3) + lane;           // TMEM lane == tile row (a warp may only touch lanes 32*(warp%4)..)
     const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
-    const uint32_t tacc = tmem_base + tlane + (uint32_t)g * 128u;
+    const bool tracer = (warp == CH_WG_EPI0 + 4 * g);
     const float4* wa4 = reinterpret_cast<const float4*>(sparams + P.w_alpha_off);
     const float4* wr4 = reinterpret_cast<const float4*>(sparams + P.w_rgb_off);
-    uint32_t d_phase = 0, aux_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    uint32_t d_phase = 0, aux_phase = 0;              // d_phase: bit per accumulator region
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int64_t m = tile * TROWS + row;
       uint8_t* rec = TRAIN ? stash + tile * (int64_t)P.rec_bytes : nullptr;
       float alpha = 0.f;
       for (int s = 0; s < C.nsteps; ++s) {
-        const ChainStep& S_ = C.steps[s];
-        int half;
-        if (S_.nhalf == 2) half = g;
-        else if (S_.d0 == g) half = 0;
-        else continue;
-        mbar_wait(&B.d_ready[g], d_phase); d_phase ^= 1;
-        tc_fence_after();
-        uint32_t ra[32], rb2[32], pw[16];
-        tmem_ld32(tacc, ra);
-        if (S_.epi != FE_VIEWS) {
-          const uint32_t a_dst = tmem_base + tlane + 256u + (uint32_t)S_.a_out * 128u + (uint32_t)half * 64u;
-          const int col0 = half * 128;
-          uint32_t mbits[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t (&r)[32] = (c & 1) ? rb2 : ra;
+        const ChainStep S_ = C.steps[s];
+        const float* sbias = sparams + P.bias_off + s * TW;
+        for (int h = 0; h < S_.nhalf; ++h) {
+          const int reg = (h == 0) ? S_.d0 : 1;
+          mbar_wait(&B.d_ready[reg], (d_phase >> reg) & 1u); d_phase ^= (1u << reg);
+          tc_fence_after();
+          if (tracer) chain_trace(C, it, s, (g ? 12 : 4) + 4 * h * (1 - g));
+          const uint32_t tacc = tmem_base + tlane + (uint32_t)reg * 128u + 64u * g;
+          const int col0 = h * 128 + 64 * g;          // first output column of this warpgroup's share
+          uint32_t r0[32], r1[32], pw[16];
+          if (!(C.debug & 4)) {
+            tmem_ld32(tacc, r0);
+            tmem_ld32(tacc + 32, r1);
             tmem_ld_wait();
-            if (c < 3) tmem_ld32(tacc + 32 * (c + 1), (c & 1) ? ra : rb2);
-            else chain_release_acc(B, g, lane);        // the whole region is in registers: next layer may overwrite it
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { r0[j] = 0; r1[j] = 0; }
+          }
+          chain_release_acc(B, reg, lane);            // my share is in registers: the issuer may overwrite the region
+          if (tracer && g == 0) chain_trace(C, it, s, 5 + 4 * h);
+          uint32_t mbits[2];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t (&r)[32] = c ? r1 : r0;
+            const int col = col0 + 32 * c;
+            {
+              const float4* b4 = reinterpret_cast<const float4*>(sbias + col);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 bb = b4[j4];
+                r[4 * j4 + 0] = __float_as_uint(__uint_as_float(r[4 * j4 + 0]) + bb.x);
+                r[4 * j4 + 1] = __float_as_uint(__uint_as_float(r[4 * j4 + 1]) + bb.y);
+                r[4 * j4 + 2] = __float_as_uint(__uint_as_float(r[4 * j4 + 2]) + bb.z);
+                r[4 * j4 + 3] = __float_as_uint(__uint_as_float(r[4 * j4 + 3]) + bb.w);
+              }
+            }
             if (TRAIN && S_.epi != FE_FEATURE) mbits[c] = sign_bits(r);
             if (S_.epi == FE_TRUNK_LAST) {
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 w4 = wa4[((col0 + 32 * c) >> 2) + j4];
+                const float4 w4 = wa4[(col >> 2) + j4];
                 alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), w4.x, alpha);
                 alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f), w4.y, alpha);
                 alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), w4.z, alpha);
                 alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f), w4.w, alpha);
               }
             }
-            if (S_.epi == FE_FEATURE) pack_chunk<false>(r, pw);
-            else pack_chunk<true>(r, pw);
-            tmem_st16(a_dst + 16 * c, pw);
-            if (TRAIN) store_chunk_global(rec + S_.off0, col0 + 32 * c, row, pw);
-            if (c & 1) chain_publish(B, half * 2 + (c >> 1), lane);
-          }
-          if (TRAIN && S_.epi != FE_FEATURE)
-            *reinterpret_cast<uint4*>(rec + S_.off1 + row * 32 + half * 16) =
-                make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-          if (S_.epi == FE_TRUNK_LAST && g == 0) {     // sigma partial sum of columns 0..127 -> warpgroup 1
-            s_alpha[row] = alpha;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&B.aux);
-          }
-        } else {
-          // views layer (always warpgroup 1): ReLU, rgb head, output
-          mbar_wait(&B.aux, aux_phase); aux_phase ^= 1;
-          alpha += s_alpha[row];
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-          uint32_t mbits[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t (&r)[32] = (c & 1) ? rb2 : ra;
-            tmem_ld_wait();
-            if (c < 3) tmem_ld32(tacc + 32 * (c + 1), (c & 1) ? ra : rb2);
-            else chain_release_acc(B, g, lane);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w0 = wr4[8 * c + j4], w1 = wr4[32 + 8 * c + j4], w2 = wr4[64 + 8 * c + j4];
-              const float v0 = fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), v1 = fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f);
-              const float v2 = fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), v3 = fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f);
-              c0 = fmaf(v0, w0.x, c0); c0 = fmaf(v1, w0.y, c0); c0 = fmaf(v2, w0.z, c0); c0 = fmaf(v3, w0.w, c0);
-              c1 = fmaf(v0, w1.x, c1); c1 = fmaf(v1, w1.y, c1); c1 = fmaf(v2, w1.z, c1); c1 = fmaf(v3, w1.w, c1);
-              c2 = fmaf(v0, w2.x, c2); c2 = fmaf(v1, w2.y, c2); c2 = fmaf(v2, w2.z, c2); c2 = fmaf(v3, w2.w, c2);
-            }
-            if (TRAIN) {
-              mbits[c] = sign_bits(r);
-              pack_chunk<true>(r, pw);
-              store_chunk_global(rec + S_.off0, 32 * c, row, pw);
+            if (S_.epi != FE_VIEWS) {
+              if (S_.epi == FE_FEATURE) pack_chunk<false>(r, pw);
+              else pack_chunk<true>(r, pw);
+              if (!(C.debug & 4)) tmem_st16(tmem_base + tlane + 256u + (uint32_t)S_.a_out * 128u + (uint32_t)(col >> 1), pw);
+              if (TRAIN) store_chunk_global(rec + S_.off0, col, row, pw);
             }
           }
-          if (m < M) {
-            const float* bh = sparams + P.b_head_off;
-            reinterpret_cast<float4*>(out)[m] = make_float4(c0 + bh[1], c1 + bh[2], c2 + bh[3], alpha + bh[0]);
+          if (S_.epi != FE_VIEWS) {
+            chain_publish(B, S_.a_out, h, lane);
+            if (tracer) chain_trace(C, it, s, g ? 13 : 6 + 4 * h);
+            if (TRAIN && S_.epi != FE_FEATURE)
+              *reinterpret_cast<uint2*>(rec + S_.off1 + row * 32 + (col0 >> 5) * 4) = make_uint2(mbits[0], mbits[1]);
+          } else {
+            // views layer (single half): ReLU, rgb head partial sums over my 64 columns; warpgroup 1 combines
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t (&r)[32] = c ? r1 : r0;
+              const int col = col0 + 32 * c;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 w0 = wr4[(col >> 2) + j4], w1 = wr4[32 + (col >> 2) + j4], w2 = wr4[64 + (col >> 2) + j4];
+                const float v0 = fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), v1 = fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f);
+                const float v2 = fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), v3 = fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f);
+                c0 = fmaf(v0, w0.x, c0); c0 = fmaf(v1, w0.y, c0); c0 = fmaf(v2, w0.z, c0); c0 = fmaf(v3, w0.w, c0);
+                c1 = fmaf(v0, w1.x, c1); c1 = fmaf(v1, w1.y, c1); c1 = fmaf(v2, w1.z, c1); c1 = fmaf(v3, w1.w, c1);
+                c2 = fmaf(v0, w2.x, c2); c2 = fmaf(v1, w2.y, c2); c2 = fmaf(v2, w2.z, c2); c2 = fmaf(v3, w2.w, c2);
+              }
+              if (TRAIN) {
+                pack_chunk<true>(r, pw);
+                store_chunk_global(rec + S_.off0, col, row, pw);
+              }
+            }
+            if (TRAIN) *reinterpret_cast<uint2*>(rec + S_.off1 + row * 16 + (col0 >> 5) * 4) = make_uint2(mbits[0], mbits[1]);
+            if (g == 0) {
+              s_part[row] = make_float4(c0, c1, c2, alpha);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&B.aux);
+            } else {
+              mbar_wait(&B.aux, aux_phase); aux_phase ^= 1;
+              const float4 o = s_part[row];
+              if (m < M) {
+                const float* bh = sparams + P.b_head_off;
+                reinterpret_cast<float4*>(out)[m] =
+                    make_float4(c0 + o.x + bh[1], c1 + o.y + bh[2], c2 + o.z + bh[3], alpha + o.w + bh[0]);
+              }
+            }
           }
-          if (TRAIN)
-            *reinterpret_cast<uint4*>(rec + S_.off1 + row * 16) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == CH_WARP_MMA0) tmem_dealloc(tmem_base, 512);
 }
 
-static size_t fwd_smem_bytes(const FwdPlan& P) { return (size_t)ChSmem::PARAMS + (size_t)P.nparam_floats * 4; }
+static size_t fwd_smem_bytes(const FwdPlan& P) { return (size_t)ChSmem::X160 + (size_t)P.nparam_floats * 4; }
 
 // head weights gathered into one contiguous float block: w_alpha[256] | w_rgb[3][128] | b_alpha, b_rgb[3]
 __global__ void gather_fwd_params_kernel(const float* __restrict__ params, float* __restrict__ dst, MlpLayout L,
@@ -346,9 +365,12 @@ __global__ void gather_fwd_params_kernel(const float* __restrict__ params, float
   float v;
   if (i < P.w_rgb_off) v = params[L.alpha_w + (i - P.w_alpha_off)];
   else if (i < P.b_head_off) v = params[L.rgb_w + (i - P.w_rgb_off)];
-  else {
+  else if (i < P.bias_off) {
     int c = i - P.b_head_off;
     v = (c == 0) ? params[L.alpha_b] : params[L.rgb_b + c - 1];
+  } else {
+    const int c = i - P.bias_off, s = c / TW, n = c - s * TW;
+    v = (s < L.D) ? params[L.pts_b[s] + n] : (s == L.D ? params[L.feat_b + n] : params[L.views_b + n]);
   }
   dst[i] = v;
 }
@@ -417,7 +439,7 @@ int lush_mlp_tc_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
   const int64_t M = R * S;
   const int64_t ntiles = (M + TROWS - 1) / TROWS;
   const size_t smem = fwd_smem_bytes(P);
-  LUSH_REQUIRE(smem + 2048 <= 227 * 1024, "mlp_fwd(tc): shared memory budget exceeded (%zu)", smem);
+  LUSH_REQUIRE(smem + 1024 <= 227 * 1024, "mlp_fwd(tc): shared memory budget exceeded (%zu)", smem);
   int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   if (stash != nullptr) {
     rc = check_cuda(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -436,4 +458,10 @@ int lush_mlp_tc_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
   }
   LUSH_LAUNCH_CHECK("mlp_tc_fwd");
   return 0;
+}
+
+extern "C" int lush_debug_read_chain_trace(long long* host_out, int n) {   // forward kernel's trace (this translation unit)
+  using namespace lush;
+  LUSH_REQUIRE(host_out && n > 0 && n <= CH_MAX_STEPS * 16, "read_chain_trace: bad arguments");
+  return check_cuda(cudaMemcpyFromSymbol(host_out, g_chain_trace, sizeof(long long) * n), "read_chain_trace");
 }

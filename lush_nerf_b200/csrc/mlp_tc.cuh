@@ -38,7 +38,7 @@ struct FwdPlan {
   FwdStep steps[MAX_STEPS];
   // smem parameter block (floats): w_alpha[256], w_rgb[3][128], b_alpha, b_rgb[3]
   // (layer biases ride in the weight stream as one extra K=16 slice per step against a ones column)
-  int w_alpha_off, w_rgb_off, b_head_off, nparam_floats;
+  int w_alpha_off, w_rgb_off, b_head_off, bias_off, nparam_floats;   // bias_off: step s -> [bias_off + s*256, +N)
   // stash record (bytes per tile)
   int rec_bytes, rec_encp, rec_h0, rec_feat, rec_encv, rec_hv, rec_mask, rec_maskv;
   int64_t wstream_bytes;
@@ -75,6 +75,7 @@ static inline void make_fwd_plan(const MlpLayout& L, FwdPlan& P) {
   P.w_alpha_off = boff; boff += TW;
   P.w_rgb_off = boff; boff += 3 * 128;
   P.b_head_off = boff; boff += 4;
+  P.bias_off = boff; boff += (L.D + 1) * TW + 128;   // pts_linears[0..D-1], feature_linear, views_linears[0]
   P.nparam_floats = boff;
   P.wstream_bytes = wbytes;
   int off = 0;

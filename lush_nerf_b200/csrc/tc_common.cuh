@@ -57,16 +57,26 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must become a launch failure (trap), never a hung GPU.
+// The poll loop lives inside one asm block (block-scoped labels), so the compiler does not wrap every wait in
+// convergence-barrier bookkeeping (BSSY/BSYNC/BMOV) -- that overhead dominated the single-thread MMA issue loops.
+// try_wait suspends the thread in hardware for a bounded time slice per attempt; 2^22 failed attempts is seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("lush tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-             threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LAB_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 q, n, 0x400000;\n\t"
+      "@q bra LAB_WAIT;\n\t"
+      "trap;\n\t"
+      "LAB_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 
 // ---------------------------------------------------------------- bulk async copies (TMA engine, 1-D)

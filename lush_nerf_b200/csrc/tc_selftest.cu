@@ -94,6 +94,82 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half* __restri
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---- tensor-pipe micro-benchmark (tools/bench_umma.py): one CTA, one issuing thread, `iters` back-to-back
+// tcgen05.mma (M=128, K=16) with zeroed operands; returns elapsed SM cycles from first issue to completion.
+//   N        : MMA N (64 | 128 | 256)
+//   nacc     : number of accumulator regions used round-robin (1 = every MMA depends on the previous one)
+//   a_tmem   : 1 = A operand from tensor memory (TS mode), 0 = from shared memory (SS mode)
+__device__ __forceinline__ uint32_t desc_lo_(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__global__ void __launch_bounds__(512) tc_microbench_kernel(long long* __restrict__ out, int N, int nacc, int a_tmem,
+                                                            int iters, int flags) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar, bar2, bar3;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int stop_flag;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) stop_flag = 0;
+  for (uint32_t i = tid * 16; i < 4096u + 256u * 32u; i += 512 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); mbar_init(&bar3, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int issuer_warp = (flags & 16) ? 15 : 0;
+  if (warp != issuer_warp && (flags & 8)) {   // busy neighbours: dependent FMA chains + shared-memory loads
+    float a = (float)tid, b = 1.0001f;
+    while (!stop_flag) {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) a = fmaf(a, b, reinterpret_cast<float*>(smem)[(tid + k) & 1023]);
+    }
+    if (a == 12345.f) out[3] = 1;
+  }
+  if (warp == issuer_warp) {   // converged warp, one elected lane issues blocks of 8 MMAs (as the product kernels do)
+    const uint32_t idesc = make_idesc_f16(128, N, 0, 0);
+    const uint32_t a_lo = desc_lo_(smem_u32(smem), 128u * 16u), b_lo = desc_lo_(smem_u32(smem) + 4096u, (uint32_t)N * 16u);
+    const uint32_t hi = (128u >> 4) | (1u << 14);
+    const uint32_t d0 = tmem_base, d1 = tmem_base + (nacc > 1 ? (uint32_t)N : 0u);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 8) {
+      if (flags & 4) mbar_wait(&bar3, 1);      // already-complete phase: pure wait latency
+      if (flags & 2) tc_fence_after();
+      uint32_t e;
+      asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(e));
+      if (e) {
+        if (a_tmem) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 db, {%2, %3};\n\t"
+                         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"((k & 1) ? d1 : d0),
+                         "r"(tmem_base + 448u), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 da, {%1, %3};\n\t"
+                         "mov.b64 db, {%2, %3};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(
+                             (k & 1) ? d1 : d0),
+                         "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
+        }
+        if (flags & 1) umma_commit(&bar2);
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if ((tid & 31) == 0) umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if ((tid & 31) == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    stop_flag = 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace lush
 
 extern "C" int lush_tc_selftest(const void* a_blob, const void* b_blob, float* d_out, int N, int K, int a_mode,
@@ -109,5 +185,15 @@ extern "C" int lush_tc_selftest(const void* a_blob, const void* b_blob, float* d
   tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)a_blob, (const __half*)b_blob, d_out,
                                                              N, K, a_mode, b_mode, swap_lbo_sbo);
   LUSH_LAUNCH_CHECK("tc_selftest");
+  return 0;
+}
+
+extern "C" int lush_tc_microbench(long long* out_cycles, int N, int nacc, int a_tmem, int iters, int flags, void* stream) {
+  using namespace lush;
+  LUSH_REQUIRE(out_cycles && (N == 64 || N == 128 || N == 256) && nacc >= 1 && nacc <= 2 && nacc * N <= 384 && iters > 0 && iters % 8 == 0,
+               "tc_microbench: bad arguments");
+  const size_t smem = 4096 + 256 * 32;
+  tc_microbench_kernel<<<1, 512, smem, (cudaStream_t)stream>>>(out_cycles, N, nacc, a_tmem, iters, flags);
+  LUSH_LAUNCH_CHECK("tc_microbench");
   return 0;
 }

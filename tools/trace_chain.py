@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Timeline of one tile of the fused forward chain kernel (CTA 0, third tile): LUSH_CHAIN_DEBUG=2 python tools/trace_chain.py"""
+import ctypes, os, sys
+os.environ["LUSH_CHAIN_DEBUG"] = os.environ.get("LUSH_CHAIN_DEBUG", "2")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from lush_nerf_b200 import _lib, ops
+from oracle import lush_oracle as O
+DEV = "cuda"
+R, S = 8192, 128
+nets = O.det_nets()
+flat = torch.cat([nets["coarse"][n].reshape(-1) for n, _ in O.mlp_param_shapes(8, 256, 63, 27, 4)]).to(DEV)
+views, off = [], 0
+for _, shp in O.mlp_param_shapes(8, 256, 63, 27, 4):
+    n = int(np.prod(shp)); views.append(flat[off:off + n].view(shp)); off += n
+desc = _lib.MlpDesc(8, 256, 10, 4, 4, 0)
+rb = torch.zeros(R, 11, device=DEV); rb[:, :3] = torch.rand(R, 3, device=DEV); rb[:, 3:6] = torch.randn(R, 3, device=DEV) * 0.3
+rb[:, 8:11] = torch.nn.functional.normalize(torch.randn(R, 3, device=DEV), dim=-1)
+z = torch.rand(R, S, device=DEV).sort(-1)[0]
+with torch.no_grad():
+    for _ in range(2):
+        ops.mlp_apply(rb, z, desc, 1, flat, views)
+torch.cuda.synchronize()
+n = 12 * 16
+buf = (ctypes.c_longlong * n)()
+_lib.check(_lib.lib().lush_debug_read_chain_trace(buf, n), "trace")
+t = np.array(buf[:], dtype=np.int64).reshape(12, 16)
+t0 = t[0][t[0] > 0].min()
+names = ["h0.iss0", "h0.iss1", "h1.iss0", "h1.iss1", "h0.drdy", "h0.rel", "h0.pub", "-", "h1.drdy", "h1.rel", "h1.pub", "-", "w1h0.drdy", "w1.pub", "h0.item0", "h1.item0"]
+print("step " + " ".join(f"{x:>10s}" for x in names))
+for s in range(11):
+    print(f"{s:4d} " + " ".join(f"{(t[s][k] - t0) if t[s][k] > 0 else -1:10d}" for k in range(16)))

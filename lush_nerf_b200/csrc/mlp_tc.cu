@@ -4,8 +4,8 @@
 // models/lushnerf.py:234-266 (mlpforward) for W = 256 networks.
 //
 // The kernel is one instance of the chain skeleton in mlp_chain.cuh (read that header first):
-//   steps 0..D-1   trunk layers (gamma(x) via SS-mode slices, hidden state via TS-mode slices straight from
-//                  tensor memory); fp32 bias add and ReLU fused into the fp16 conversion of the epilogue
+//   steps 0..D-1   trunk layers: bias via a ones-column K=16 slice, gamma(x) and the hidden state as shared-memory
+//                  A operands; ReLU fused into the fp16 conversion of the epilogue
 //   step D         feature_linear (no activation)
 //   step D+1       views_linears[0] on [feature | gamma(viewdirs)], N = 128, accumulator region 1
 // The sigma head (256->1) and rgb head (128->3) are fp32 register dot products over the accumulators in the
@@ -25,11 +25,12 @@ static void make_fwd_chain(const MlpLayout& L, const FwdPlan& P, ChainPlan& C) {
   int n = 0;
   for (int i = 0; i < L.D; ++i) {
     ChainStep& s = C.steps[n];
-    s.nhalf = 2; s.d0 = 0; s.NH = 128; s.pre16 = 0; s.enc_src = 0;
+    s.N = TW; s.pre16 = 1; s.enc_src = 0;
     const bool enc = (i == 0) || (L.skip >= 0 && i == L.skip + 1);
     s.enc_slices = enc ? 2 : 0;
     s.h_slices = (i == 0) ? 0 : TW / KS;
-    s.a_in = (int8_t)(n & 1); s.wait_a = (i > 0); s.a_out = (int8_t)((n + 1) & 1);
+    s.wait_a = (i > 0); s.writes_a = 1;
+    s.free_enc = (L.skip >= 0 ? (i == L.skip + 1) : (i == 0)) ? 1 : 0;   // last step that reads gamma(x)
     s.epi = (i == L.D - 1) ? FE_TRUNK_LAST : FE_TRUNK;
     s.p0 = (int16_t)i; s.p1 = 0;
     s.off0 = P.rec_h0 + i * H_BYTES;
@@ -37,27 +38,35 @@ static void make_fwd_chain(const MlpLayout& L, const FwdPlan& P, ChainPlan& C) {
     ++n;
   }
   { ChainStep& s = C.steps[n];
-    s.nhalf = 2; s.d0 = 0; s.NH = 128; s.pre16 = 0; s.enc_src = 0; s.enc_slices = 0; s.h_slices = TW / KS;
-    s.a_in = (int8_t)(n & 1); s.wait_a = 1; s.a_out = (int8_t)((n + 1) & 1);
+    s.N = TW; s.pre16 = 1; s.enc_src = 0; s.enc_slices = 0; s.h_slices = TW / KS;
+    s.wait_a = 1; s.writes_a = 1; s.free_enc = 0;
     s.epi = FE_FEATURE; s.p0 = 0; s.p1 = 0; s.off0 = P.rec_feat; s.off1 = 0;
     ++n; }
   { ChainStep& s = C.steps[n];
-    s.nhalf = 1; s.d0 = 1; s.NH = 128; s.pre16 = 0; s.enc_src = 1; s.enc_slices = 1; s.h_slices = TW / KS;
-    s.a_in = (int8_t)(n & 1); s.wait_a = 1; s.a_out = -1;
+    s.N = 128; s.pre16 = 1; s.enc_src = 1; s.enc_slices = 1; s.h_slices = TW / KS;
+    s.wait_a = 1; s.writes_a = 0; s.free_enc = 2;
     s.epi = FE_VIEWS; s.p0 = 0; s.p1 = 0; s.off0 = P.rec_hv; s.off1 = P.rec_maskv;
     ++n; }
   C.nsteps = n;
   chain_finish_plan(C);
 }
 
-// One block row (blockIdx.y) per step; one thread per packed fp16 element.  Per half h of a step the stream holds
-//   [bias block NH x 16 (column 0 = bias)] [enc block NH x 32*enc_slices] [hidden blocks NH x 128 ...]
-// each block in the tile-canonical layout with NH rows: offset(n, k) = (k/8)*(NH*16) + n*16 + (k%8)*2.
+// shared-memory map of the forward kernel behind the ring and the activation tile
+struct FwdSmem {
+  static constexpr int ENC = ChSmem::FREE0;                 // [128 x 64] gamma(x), single buffer
+  static constexpr int ENCV = ENC + ENC_BYTES;              // 2 x [128 x 32] gamma(viewdirs)
+  static constexpr int ONES = ENCV + 2 * ENCV_BYTES;        // [128 x 16], column 0 = 1 (bias operand)
+  static constexpr int PARAMS = ONES + CH_X16_BYTES;        // head weights (fp32)
+};
+
+// One block row (blockIdx.y) per step; one thread per packed fp16 element.  The stream of a step holds
+//   [bias block N x 16 (column 0 = bias)] [enc block N x 32*enc_slices] [hidden blocks N x 64 ...]
+// each block in the tile-canonical layout with N rows: offset(n, k) = (k/8)*(N*16) + n*16 + (k%8)*2.
 struct PackJob {
   int64_t out_off;   // byte offset of the step in the stream
   int64_t w_off;     // float offset of the [N, fan_in] weight in the flat params
   int64_t b_off;     // float offset of the bias [N]
-  int fan_in, nhalf, NH, pre16, enc_slices, h_slices;
+  int fan_in, N, pre16, enc_slices, h_slices;
   int enc_real, enc_col0, main_col0;   // nn.Linear column of encoding channel 0 / hidden unit 0
 };
 struct PackPlan {
@@ -68,33 +77,31 @@ struct PackPlan {
 __global__ void pack_fwd_weights_kernel(const float* __restrict__ params, __half* __restrict__ stream,
                                         PackPlan plan) {
   const PackJob& J = plan.jobs[blockIdx.y];
-  const int n_pre = J.NH * 16 * J.pre16, n_enc = J.NH * KS * J.enc_slices;
-  const int per_half = n_pre + n_enc + J.NH * KS * J.h_slices;
-  const int total = J.nhalf * per_half;
+  const int n_pre = J.N * 16 * J.pre16, n_enc = J.N * KS * J.enc_slices;
+  const int total = n_pre + n_enc + J.N * KS * J.h_slices;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int h = e / per_half;
-    int r = e - h * per_half;
+    int r = e;
     float v = 0.f;
     if (r < n_pre) {
-      const int g = r / (J.NH * 8), rem = r - g * J.NH * 8;
+      const int g = r / (J.N * 8), rem = r - g * J.N * 8;
       const int n = rem >> 3, k8 = rem & 7;
-      if (g == 0 && k8 == 0) v = params[J.b_off + h * J.NH + n];
+      if (g == 0 && k8 == 0) v = params[J.b_off + n];
     } else {
       r -= n_pre;
       int col = -1, n;
       if (r < n_enc) {
-        const int kk8 = r / (J.NH * 8), rem = r - kk8 * J.NH * 8;
+        const int kk8 = r / (J.N * 8), rem = r - kk8 * J.N * 8;
         n = rem >> 3;
         const int k = kk8 * 8 + (rem & 7);
         if (k < J.enc_real) col = J.enc_col0 + k;
       } else {
         r -= n_enc;
-        const int blk = r / (J.NH * 128), rem = r - blk * J.NH * 128;
-        const int kk8 = rem / (J.NH * 8), rem2 = rem - kk8 * J.NH * 8;
+        const int blk = r / (J.N * 64), rem = r - blk * J.N * 64;
+        const int kk8 = rem / (J.N * 8), rem2 = rem - kk8 * J.N * 8;
         n = rem2 >> 3;
-        col = J.main_col0 + blk * 128 + kk8 * 8 + (rem2 & 7);
+        col = J.main_col0 + blk * 64 + kk8 * 8 + (rem2 & 7);
       }
-      if (col >= 0) v = params[J.w_off + (int64_t)(h * J.NH + n) * J.fan_in + col];
+      if (col >= 0) v = params[J.w_off + (int64_t)n * J.fan_in + col];
     }
     stream[J.out_off / 2 + e] = __float2half_rn(v);
   }
@@ -107,7 +114,7 @@ static void make_pack_plan(const MlpLayout& L, const ChainPlan& C, PackPlan& K) 
     const ChainStep& st = C.steps[s];
     PackJob& J = K.jobs[s];
     J.out_off = off;
-    J.nhalf = st.nhalf; J.NH = st.NH; J.pre16 = st.pre16; J.enc_slices = st.enc_slices; J.h_slices = st.h_slices;
+    J.N = st.N; J.pre16 = st.pre16; J.enc_slices = st.enc_slices; J.h_slices = st.h_slices;
     if (s < L.D) {
       J.w_off = L.pts_w[s]; J.b_off = L.pts_b[s]; J.fan_in = L.pts_in[s];
       J.enc_real = L.in_ch; J.enc_col0 = 0;
@@ -118,7 +125,7 @@ static void make_pack_plan(const MlpLayout& L, const ChainPlan& C, PackPlan& K) 
       J.w_off = L.views_w; J.b_off = L.views_b; J.fan_in = L.W + L.in_ch_v;   // [feature | views] (helpers:409)
       J.enc_real = L.in_ch_v; J.enc_col0 = L.W; J.main_col0 = 0;
     }
-    off += (int64_t)st.nhalf * chain_half_bytes(st);
+    off += chain_step_bytes(st);
   }
 }
 
@@ -191,9 +198,14 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + TROWS - 1) / TROWS;
-  float* sparams = reinterpret_cast<float*>(smem + ChSmem::X160);   // the forward has no X16 operand: params live there
+  float* sparams = reinterpret_cast<float*>(smem + FwdSmem::PARAMS);
+  const int nhead = P.bias_off;      // w_alpha | w_rgb | head biases (layer biases ride in the weight stream)
 
-  for (int i = tid; i < P.nparam_floats; i += CH_THREADS) sparams[i] = params_smem_src[i];
+  for (int i = tid; i < nhead; i += CH_THREADS) sparams[i] = params_smem_src[i];
+  // ones operand: row r -> [1, 0 x 7 | 0 x 8]: the K=16 slice that adds the bias inside the MMA
+  for (int i = tid; i < CH_X16_BYTES / 16; i += CH_THREADS)
+    *reinterpret_cast<uint4*>(smem + FwdSmem::ONES + i * 16) = (i < TROWS) ? make_uint4(0x3C00u, 0u, 0u, 0u)
+                                                                            : make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) chain_init_bars(B);
   if (warp == CH_WARP_MMA0) tmem_alloc(&tmem_base_s, 512);
   fence_proxy_async();
@@ -205,14 +217,14 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
   if (warp == CH_WARP_PRODUCER) {
     if (lane == 0) chain_producer(B, smem, wstream, C, ntiles);
   } else if (warp >= CH_WARP_MMA0) {
-    chain_mma_issuer(B, smem, tmem_base, C, ntiles, (uint32_t)(warp - CH_WARP_MMA0));
+    const ChainMap map = {(uint32_t)FwdSmem::ENC, (uint32_t)FwdSmem::ENCV, (uint32_t)ENCV_BYTES, (uint32_t)FwdSmem::ONES, 0u};
+    chain_mma_issuer(B, smem, tmem_base, C, map, ntiles, (uint32_t)(warp - CH_WARP_MMA0));
   } else if (warp < CH_WG_EPI0) {
     // =========================== prologue warpgroup: sample points + encodings of the NEXT tile ===========
     const int row = tid - CH_WG_PRO * 32;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int b = (int)(it & 1);
-      if (it >= 2) mbar_wait(&B.pro_free[b], (uint32_t)(((it >> 1) + 1) & 1));
       const int64_t m = tile * TROWS + row;
       float x0 = 0.f, x1 = 0.f, x2 = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
       if (m < M) {
@@ -225,69 +237,60 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         vx = rb[8]; vy = rb[9]; vz = rb[10];
       }
       uint8_t* rec = TRAIN ? stash + tile * (int64_t)P.rec_bytes : nullptr;
-      if (!(C.debug & 8) || it < 2) {
-      encode_row<64>(smem + ChSmem::ENC0 + b * ENC_BYTES, TRAIN ? rec + P.rec_encp : nullptr, row, x0, x1, x2, L_pts);
-      encode_row<32>(smem + ChSmem::ENCV0 + b * ENCV_BYTES, TRAIN ? rec + P.rec_encv : nullptr, row, vx, vy, vz,
-                     L_views);
-      }
+      // gamma(viewdirs) is double-buffered; gamma(x) has ONE buffer, free once the previous tile's last trunk
+      // layer that reads it (step 0 or the skip layer) has completed -- several layers before that tile ends
+      if (it >= 2) mbar_wait(&B.pro_free[b], (uint32_t)(((it >> 1) + 1) & 1));
+      encode_row<32>(smem + FwdSmem::ENCV + b * ENCV_BYTES, TRAIN ? rec + P.rec_encv : nullptr, row, vx, vy, vz, L_views);
+      if (it >= 1) mbar_wait(&B.enc_free, (uint32_t)((it + 1) & 1));
+      if (!(C.debug & 8) || it < 1)
+        encode_row<64>(smem + FwdSmem::ENC, TRAIN ? rec + P.rec_encp : nullptr, row, x0, x1, x2, L_pts);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.pro_ready[b]);
     }
   } else if (warp < CH_WARP_PRODUCER) {
     // =========================== epilogue warpgroups ===========================
-    // Both warpgroups drain every output half: warpgroup g owns columns [64g, 64g+64) of the half (two chunks of
-    // 32), loads both chunks at once, releases the accumulator, and publishes its 64 K-values of the next layer.
+    // The accumulator is drained one 64-column group per round; warpgroup g converts columns [32g, 32g+32) of the
+    // group (one tcgen05.ld.x32, software-pipelined one round ahead): activation, fp16, store into the activation
+    // tile (+ stash), publish the group.  The accumulator is released once its last chunk is in registers.
     const int g = (warp - CH_WG_EPI0) >> 2;
     const int row = 32 * (warp & 3) + lane;           // TMEM lane == tile row (a warp may only touch lanes 32*(warp%4)..)
     const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
     const bool tracer = (warp == CH_WG_EPI0 + 4 * g);
+    uint8_t* act = smem + ChSmem::ACT;
     const float4* wa4 = reinterpret_cast<const float4*>(sparams + P.w_alpha_off);
     const float4* wr4 = reinterpret_cast<const float4*>(sparams + P.w_rgb_off);
-    uint32_t d_phase = 0, aux_phase = 0;              // d_phase: bit per accumulator region
+    uint32_t d_phase = 0, aux_phase = 0, acc_sel = 0;   // d_phase: bit per accumulator
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int64_t m = tile * TROWS + row;
       uint8_t* rec = TRAIN ? stash + tile * (int64_t)P.rec_bytes : nullptr;
       float alpha = 0.f;
-      for (int s = 0; s < C.nsteps; ++s) {
+      for (int s = 0; s < C.nsteps; ++s, acc_sel ^= 1u) {
         const ChainStep S_ = C.steps[s];
-        const float* sbias = sparams + P.bias_off + s * TW;
-        for (int h = 0; h < S_.nhalf; ++h) {
-          const int reg = (h == 0) ? S_.d0 : 1;
-          mbar_wait(&B.d_ready[reg], (d_phase >> reg) & 1u); d_phase ^= (1u << reg);
-          tc_fence_after();
-          if (tracer) chain_trace(C, it, s, (g ? 12 : 4) + 4 * h * (1 - g));
-          const uint32_t tacc = tmem_base + tlane + (uint32_t)reg * 128u + 64u * g;
-          const int col0 = h * 128 + 64 * g;          // first output column of this warpgroup's share
-          uint32_t r0[32], r1[32], pw[16];
-          if (!(C.debug & 4)) {
-            tmem_ld32(tacc, r0);
-            tmem_ld32(tacc + 32, r1);
+        const int nround = S_.N >> 6;                 // 64-column groups: 256 -> 4, 128 -> 2
+        mbar_wait(&B.d_ready[acc_sel], (d_phase >> acc_sel) & 1u); d_phase ^= (1u << acc_sel);
+        tc_fence_after();
+        if (tracer) chain_trace(C, it, s, 4 + 4 * g);
+        const uint32_t tacc = tmem_base + tlane + acc_sel * 256u + 32u * g;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        uint32_t ra[32], rb2[32], pw[16];
+        tmem_ld32(tacc, ra);
+#pragma unroll 1
+        for (int rd2 = 0; rd2 < nround; rd2 += 2) {
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            const int rd = rd2 + hb;
+            uint32_t (&r)[32] = hb ? rb2 : ra;
+            const int col = 64 * rd + 32 * g;         // first output column of my chunk
             tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { r0[j] = 0; r1[j] = 0; }
-          }
-          chain_release_acc(B, reg, lane);            // my share is in registers: the issuer may overwrite the region
-          if (tracer && g == 0) chain_trace(C, it, s, 5 + 4 * h);
-          uint32_t mbits[2];
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t (&r)[32] = c ? r1 : r0;
-            const int col = col0 + 32 * c;
-            {
-              const float4* b4 = reinterpret_cast<const float4*>(sbias + col);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 bb = b4[j4];
-                r[4 * j4 + 0] = __float_as_uint(__uint_as_float(r[4 * j4 + 0]) + bb.x);
-                r[4 * j4 + 1] = __float_as_uint(__uint_as_float(r[4 * j4 + 1]) + bb.y);
-                r[4 * j4 + 2] = __float_as_uint(__uint_as_float(r[4 * j4 + 2]) + bb.z);
-                r[4 * j4 + 3] = __float_as_uint(__uint_as_float(r[4 * j4 + 3]) + bb.w);
-              }
+            if (rd + 1 < nround) tmem_ld32(tacc + 64u * (rd + 1), hb ? ra : rb2);
+            else {                                    // everything of mine is in registers
+              chain_release_acc(B, (int)acc_sel, lane);
+              if (tracer) chain_trace(C, it, s, 5 + 4 * g);
             }
-            if (TRAIN && S_.epi != FE_FEATURE) mbits[c] = sign_bits(r);
+            if (TRAIN && S_.epi != FE_FEATURE)
+              *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (col >> 5) * 4) = sign_bits(r);
             if (S_.epi == FE_TRUNK_LAST) {
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
@@ -301,22 +304,15 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
             if (S_.epi != FE_VIEWS) {
               if (S_.epi == FE_FEATURE) pack_chunk<false>(r, pw);
               else pack_chunk<true>(r, pw);
-              if (!(C.debug & 4)) tmem_st16(tmem_base + tlane + 256u + (uint32_t)S_.a_out * 128u + (uint32_t)(col >> 1), pw);
-              if (TRAIN) store_chunk_global(rec + S_.off0, col, row, pw);
-            }
-          }
-          if (S_.epi != FE_VIEWS) {
-            chain_publish(B, S_.a_out, h, lane);
-            if (tracer) chain_trace(C, it, s, g ? 13 : 6 + 4 * h);
-            if (TRAIN && S_.epi != FE_FEATURE)
-              *reinterpret_cast<uint2*>(rec + S_.off1 + row * 32 + (col0 >> 5) * 4) = make_uint2(mbits[0], mbits[1]);
-          } else {
-            // views layer (single half): ReLU, rgb head partial sums over my 64 columns; warpgroup 1 combines
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t (&r)[32] = c ? r1 : r0;
-              const int col = col0 + 32 * c;
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(act + ((col >> 3) + q) * (TROWS * 16) + row * 16) =
+                    make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
+              chain_publish(B, rd, lane);
+              if (tracer && rd < 2) chain_trace(C, it, s, 6 + 4 * g + rd);
+              if (TRAIN) store_chunk_global(rec + S_.off0, col, row, pw);
+            } else {
+              // views layer: ReLU, rgb head partial sums over my columns; warpgroup 1 combines
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 w0 = wr4[(col >> 2) + j4], w1 = wr4[32 + (col >> 2) + j4], w2 = wr4[64 + (col >> 2) + j4];
@@ -331,19 +327,20 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                 store_chunk_global(rec + S_.off0, col, row, pw);
               }
             }
-            if (TRAIN) *reinterpret_cast<uint2*>(rec + S_.off1 + row * 16 + (col0 >> 5) * 4) = make_uint2(mbits[0], mbits[1]);
-            if (g == 0) {
-              s_part[row] = make_float4(c0, c1, c2, alpha);
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&B.aux);
-            } else {
-              mbar_wait(&B.aux, aux_phase); aux_phase ^= 1;
-              const float4 o = s_part[row];
-              if (m < M) {
-                const float* bh = sparams + P.b_head_off;
-                reinterpret_cast<float4*>(out)[m] =
-                    make_float4(c0 + o.x + bh[1], c1 + o.y + bh[2], c2 + o.z + bh[3], alpha + o.w + bh[0]);
-              }
+          }
+        }
+        if (S_.epi == FE_VIEWS) {
+          if (g == 0) {
+            s_part[row] = make_float4(c0, c1, c2, alpha);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&B.aux);
+          } else {
+            mbar_wait(&B.aux, aux_phase); aux_phase ^= 1;
+            const float4 o = s_part[row];
+            if (m < M) {
+              const float* bh = sparams + P.b_head_off;
+              reinterpret_cast<float4*>(out)[m] =
+                  make_float4(c0 + o.x + bh[1], c1 + o.y + bh[2], c2 + o.z + bh[3], alpha + o.w + bh[0]);
             }
           }
         }
@@ -355,7 +352,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
   if (warp == CH_WARP_MMA0) tmem_dealloc(tmem_base, 512);
 }
 
-static size_t fwd_smem_bytes(const FwdPlan& P) { return (size_t)ChSmem::X160 + (size_t)P.nparam_floats * 4; }
+static size_t fwd_smem_bytes(const FwdPlan& P) { return (size_t)FwdSmem::PARAMS + (size_t)P.bias_off * 4; }
 
 // head weights gathered into one contiguous float block: w_alpha[256] | w_rgb[3][128] | b_alpha, b_rgb[3]
 __global__ void gather_fwd_params_kernel(const float* __restrict__ params, float* __restrict__ dst, MlpLayout L,

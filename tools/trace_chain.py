@@ -26,7 +26,7 @@ buf = (ctypes.c_longlong * n)()
 _lib.check(_lib.lib().lush_debug_read_chain_trace(buf, n), "trace")
 t = np.array(buf[:], dtype=np.int64).reshape(12, 16)
 t0 = t[0][t[0] > 0].min()
-names = ["h0.iss0", "h0.iss1", "h1.iss0", "h1.iss1", "h0.drdy", "h0.rel", "h0.pub", "-", "h1.drdy", "h1.rel", "h1.pub", "-", "w1h0.drdy", "w1.pub", "h0.item0", "h1.item0"]
+names = ["i0.start", "i0.end", "i1.start", "i1.end", "w0.drdy", "w0.rel", "w0.pub0", "w0.pub1", "w1.drdy", "w1.rel", "w1.pub0", "w1.pub1"]
 print("step " + " ".join(f"{x:>10s}" for x in names))
 for s in range(11):
-    print(f"{s:4d} " + " ".join(f"{(t[s][k] - t0) if t[s][k] > 0 else -1:10d}" for k in range(16)))
+    print(f"{s:4d} " + " ".join(f"{(t[s][k] - t0) if t[s][k] > 0 else -1:10d}" for k in range(12)))

@@ -223,7 +223,6 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
       const uint32_t e_lo = S.enc_src ? encv_lo : enc_lo;
       const uint32_t merge = (uint32_t)chain_merge_h0(S);
       const uint32_t nblk = (uint32_t)chain_nblocks(S);
-      const uint32_t ngrp = (uint32_t)S.h_slices >> 1;
       const uint32_t tacc = tmem_base + acc_sel * 256u;
       uint32_t seen = 0;                 // activation groups whose completion this issuer has observed this step
       chain_trace(P, it, s, 2 * (int)my);
@@ -261,8 +260,8 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
         if (++stage == CH_NSTAGE) { stage = 0; phase ^= 1u; }
       }
       // per-step bookkeeping (both issuers observe every barrier phase they track, in order)
-      if (S.wait_a) {
-        for (uint32_t j = 0; j < ngrp; ++j)
+      if (S.wait_a) {   // every writer publishes all four groups (a 128-wide one publishes 2 and 3 as empty)
+        for (uint32_t j = 0; j < 4u; ++j)
           if (!((seen >> j) & 1u)) mbar_wait(&B.a_ready[j], a_par);
         a_par ^= 1u;
       }

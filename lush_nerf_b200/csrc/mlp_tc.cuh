@@ -138,6 +138,21 @@ __device__ __forceinline__ uint32_t relu_mask_apply(uint32_t packed, uint32_t m)
 }
 __device__ __forceinline__ bool relu_mask_test(uint32_t m, int c) { return (m >> relu_mask_pos(c)) & 1u; }
 
+template <bool RELU>
+__device__ __forceinline__ void pack_chunk(const uint32_t (&r)[32], uint32_t (&pw)[16]) {
+#pragma unroll
+  for (int w = 0; w < 16; ++w)
+    pw[w] = RELU ? pack_h2_relu(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]))
+                 : pack_h2(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]));
+}
+// 32 columns (4 groups of 8) of one row of a [128 x *] tile-canonical blob in global memory; c = first column
+__device__ __forceinline__ void store_chunk_global(uint8_t* blob, int c, int row, const uint32_t (&pw)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(blob + ((c >> 3) + g) * (TROWS * 16) + row * 16) =
+        make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -12,91 +12,99 @@
 //     tiles and are flushed once per chunk with fp32 atomics into the flat gradient buffer.  Bias gradients
 //     are column sums taken from the dZ stage in shared memory by the otherwise idle epilogue warps.
 //  3. small SIMT kernels: head gradients (sigma / rgb heads), per-ray reduction of d/d(o, d, viewdirs).
-#include "mlp_tc.cuh"
+#include "mlp_chain.cuh"
 
 namespace lush {
 
-constexpr int BWD_THREADS = FWD_THREADS;   // same warp roles as the forward kernel
 constexpr float kGradTarget = 32.f;   // scaled max |g_out|
 
-enum BwdEpi { BEPI_FEAT = 0, BEPI_TRUNK = 1, BEPI_ENC_SAVE = 2, BEPI_ENC_FINAL = 3 };
+enum BwdEpi { BE_VIEWS = 0, BE_FEAT = 1, BE_TRUNK = 2, BE_ENC = 3 };
 
-struct BwdStep {
-  int N;           // output columns of this dgrad GEMM (256 or 64)
-  int nslices;     // reduction slices of 32 over the producing layer's output units
-  int epi;         // BwdEpi
-  int mask_layer;  // BEPI_TRUNK: trunk layer whose ReLU gates the result
-  int add_alpha;   // BEPI_TRUNK: add g_sigma * w_alpha (gradient into the last trunk activation)
-  int dz_off;      // byte offset inside the gstash record receiving the epilogue output (-1: none)
-};
-
+// gstash record (per 128-sample tile): dZv [128 x 128] | dZf [128 x 256] | dZ_0 .. dZ_{D-1} [128 x 256] each
 struct BwdPlan {
-  int nsteps;
-  BwdStep steps[MAX_STEPS + 2];
-  int has_skip_enc;     // an ENC_SAVE step exists (its result is added in ENC_FINAL)
-  int grec_bytes, grec_v, grec_f, grec_l0;   // gstash record: dZv | dZf | dZ_0 .. dZ_{D-1}
-  int64_t bstream_bytes;
+  int grec_bytes, grec_v, grec_f, grec_l0;
+  int has_enc;          // d/d gamma(x) is produced (two [128 x 64] fp16 blobs per tile: skip layer, layer 0)
 };
 
 struct BPackJob {
-  int64_t out_off, w_off;
-  int fan_in, col0, ncols_real, N, Kp;
+  int64_t out_off;      // byte offset of the step in the stream
+  int64_t w_off;        // float offset of the [rows, fan_in] weight whose TRANSPOSE is the B operand
+  int fan_in, col0, ncols_real, N, K;   // B[n][k] = W[k][col0 + n] for n < ncols_real, k < K
+  int pre_kind;         // 0: none, 1: rgb head rows (k < 3 -> w_rgb[k][n]), 2: sigma head (k == 3 -> w_alpha[n])
+  int64_t pre_off;      // float offset of that head weight
 };
 struct BPackPlan {
   int njobs;
-  BPackJob jobs[MAX_STEPS + 2];
+  BPackJob jobs[CH_MAX_STEPS];
 };
 
-static void make_bwd_plan(const MlpLayout& L, bool need_in, BwdPlan& B, BPackPlan& K) {
+// dgrad chain:  P: dZv = mask_v(G16 . Wrgb)            N=128  K=16 (pre16 only)
+//               0: g_feat = dZv . Wv[:, :W]             N=256  K=128
+//               1: dZ_{D-1} = mask(dZf . Wf + g_sigma w_alpha)     N=256  K=256 + pre16
+//               l = D-1..1: [skip layer: d gamma += dZ_l . W_l[:, :in_ch]  N=64]  dZ_{l-1} = mask(dZ_l . W_l[:, hidden])
+//               last: d gamma += dZ_0 . W_0            N=64
+static void make_bwd_chain(const MlpLayout& L, bool need_in, ChainPlan& C, BwdPlan& B, BPackPlan& K) {
   B.grec_v = 0;
   B.grec_f = HV_BYTES;
   B.grec_l0 = HV_BYTES + H_BYTES;
   B.grec_bytes = B.grec_l0 + L.D * H_BYTES;
-  B.has_skip_enc = 0;
+  B.has_enc = need_in ? 1 : 0;
   int n = 0;
   int64_t off = 0;
-  auto add = [&](int N, int Kp, int epi, int mask_layer, int add_alpha, int dz_off, int64_t w_off, int fan_in,
-                 int col0, int ncols_real) {
-    BwdStep& s = B.steps[n];
-    s.N = N; s.nslices = Kp / KS; s.epi = epi; s.mask_layer = mask_layer; s.add_alpha = add_alpha; s.dz_off = dz_off;
+  auto add = [&](int N, int pre16, int h_slices, int wait_a, int writes_a, int free_enc, int epi, int p0, int off0,
+                 int64_t w_off, int fan_in, int col0, int ncols_real, int pre_kind, int64_t pre_off) {
+    ChainStep& s = C.steps[n];
+    s.N = (int16_t)N; s.pre16 = (int8_t)pre16; s.enc_slices = 0; s.enc_src = 0; s.h_slices = (int8_t)h_slices;
+    s.wait_a = (int8_t)wait_a; s.writes_a = (int8_t)writes_a; s.free_enc = (int8_t)free_enc; s.epi = (int8_t)epi;
+    s.p0 = (int16_t)p0; s.p1 = 0; s.off0 = off0; s.off1 = 0;
     BPackJob& J = K.jobs[n];
-    J.out_off = off; J.w_off = w_off; J.fan_in = fan_in; J.col0 = col0; J.ncols_real = ncols_real; J.N = N; J.Kp = Kp;
-    off += (int64_t)N * Kp * 2;
+    J.out_off = off; J.w_off = w_off; J.fan_in = fan_in; J.col0 = col0; J.ncols_real = ncols_real; J.N = N;
+    J.K = KS * h_slices; J.pre_kind = pre_kind; J.pre_off = pre_off;
+    off += chain_step_bytes(s);
     ++n;
   };
-  // views layer: g_feat = dZv . Wv[:, 0:W]
-  add(TW, 128, BEPI_FEAT, -1, 0, B.grec_f, L.views_w, L.W + L.in_ch_v, 0, TW);
-  // feature layer: g_h_{D-1} = dZf . Wf (+ g_sigma w_alpha), ReLU mask of layer D-1
-  add(TW, TW, BEPI_TRUNK, L.D - 1, 1, B.grec_l0 + (L.D - 1) * H_BYTES, L.feat_w, L.W, 0, TW);
+  add(128, 1, 0, 0, 1, 0, BE_VIEWS, 0, B.grec_v, 0, 0, 0, 0, 1, L.rgb_w);
+  add(TW, 0, 4, 1, 1, 0, BE_FEAT, 0, B.grec_f, L.views_w, L.W + L.in_ch_v, 0, TW, 0, 0);
+  add(TW, 1, 8, 1, 1, 2, BE_TRUNK, L.D - 1, B.grec_l0 + (L.D - 1) * H_BYTES, L.feat_w, L.W, 0, TW, 2, L.alpha_w);
+  int prev_wrote = 1;
   for (int l = L.D - 1; l >= 1; --l) {
     const bool is_skip = (L.skip >= 0 && l == L.skip + 1);
     if (is_skip && need_in) {
-      add(64, TW, BEPI_ENC_SAVE, -1, 0, -1, L.pts_w[l], L.pts_in[l], 0, L.in_ch);
-      B.has_skip_enc = 1;
+      add(64, 0, 8, prev_wrote, 0, 0, BE_ENC, 0, 0, L.pts_w[l], L.pts_in[l], 0, L.in_ch, 0, 0);
+      prev_wrote = 0;
     }
-    add(TW, TW, BEPI_TRUNK, l - 1, 0, B.grec_l0 + (l - 1) * H_BYTES, L.pts_w[l], L.pts_in[l],
-        is_skip ? L.in_ch : 0, TW);
+    // the last dZ has a consumer inside the chain only when d/d gamma(x) is wanted
+    add(TW, 0, 8, prev_wrote, (l > 1 || need_in) ? 1 : 0, 0, BE_TRUNK, l - 1, B.grec_l0 + (l - 1) * H_BYTES, L.pts_w[l],
+        L.pts_in[l], is_skip ? L.in_ch : 0, TW, 0, 0);
+    prev_wrote = 1;
   }
-  if (need_in) add(64, TW, BEPI_ENC_FINAL, -1, 0, -1, L.pts_w[0], L.pts_in[0], 0, L.in_ch);
-  B.nsteps = n;
+  if (need_in) add(64, 0, 8, prev_wrote, 0, 0, BE_ENC, 1, 0, L.pts_w[0], L.pts_in[0], 0, L.in_ch, 0, 0);
+  C.nsteps = n;
   K.njobs = n;
-  B.bstream_bytes = off;
+  chain_finish_plan(C);
 }
 
-// stream element (kin, n) of a step = W[n, col0 + kin]  (B operand [N x Kp], K-major over n)
+// stream of a step: [pre16 block N x 16] [hidden blocks N x 64 ...]; element (n, k) = W[k][col0 + n]
 __global__ void pack_bwd_weights_kernel(const float* __restrict__ params, __half* __restrict__ stream,
                                         BPackPlan plan) {
   const BPackJob& J = plan.jobs[blockIdx.y];
-  const int64_t total = (int64_t)J.N * J.Kp;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int per_slice = J.N * KS;
-    int j = (int)(e / per_slice);
-    int rem = (int)(e - (int64_t)j * per_slice);
-    int g = rem / (J.N * 8);
-    int rem2 = rem - g * J.N * 8;
-    int kin = rem2 / 8, n8 = rem2 % 8;
-    int nn = j * KS + g * 8 + n8;   // producing layer's output unit (reduction index)
-    float v = (kin < J.ncols_real) ? params[J.w_off + (int64_t)nn * J.fan_in + J.col0 + kin] : 0.f;
+  const int n_pre = J.pre_kind ? J.N * 16 : 0;
+  const int total = n_pre + J.N * J.K;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (e < n_pre) {
+      const int g = e / (J.N * 8), rem = e - g * J.N * 8;
+      const int n = rem >> 3, k = g * 8 + (rem & 7);
+      if (J.pre_kind == 1) { if (k < 3) v = params[J.pre_off + (int64_t)k * J.N + n]; }
+      else if (k == 3) v = params[J.pre_off + n];
+    } else {
+      const int r = e - n_pre;
+      const int blk = r / (J.N * 64), rem = r - blk * J.N * 64;
+      const int kk8 = rem / (J.N * 8), rem2 = rem - kk8 * J.N * 8;
+      const int n = rem2 >> 3;
+      const int k = blk * 64 + kk8 * 8 + (rem2 & 7);
+      if (n < J.ncols_real) v = params[J.w_off + (int64_t)k * J.fan_in + J.col0 + n];
+    }
     stream[J.out_off / 2 + e] = __float2half_rn(v);
   }
 }
@@ -120,14 +128,6 @@ __device__ __forceinline__ float grad_scale_from(const unsigned* buf) {
   return exp2f(e);
 }
 
-struct DgSmem {
-  static constexpr int G0 = 0;
-  static constexpr int ENC0 = 2 * H_BYTES;
-  static constexpr int STAGE0 = ENC0 + 2 * ENC_BYTES;
-  static constexpr int PARAMS = STAGE0 + NSTAGE * STAGE_BYTES;   // w_alpha[256], w_rgb[384]
-  static constexpr int TOTAL = PARAMS + (TW + 384) * 4;
-};
-
 __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
@@ -137,175 +137,99 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
   }
 }
 
+// shared-memory map of the dgrad kernel behind the ring and the activation tile
+struct DgSmem {
+  static constexpr int G16 = ChSmem::FREE0;                 // 2 x [128 x 16]: (g_r, g_g, g_b, g_sigma, 0...) * scale
+  static constexpr int TOTAL = G16 + 2 * CH_X16_BYTES;
+};
+
 // ------------------------------------------------------------------------------------------------
-// stage 1: fused dgrad chain
+// stage 1: fused dgrad chain (one instance of the skeleton in mlp_chain.cuh)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BWD_THREADS, 1)
-mlp_tc_dgrad_kernel(const __half* __restrict__ bstream, const float* __restrict__ head_params,
-                    const float* __restrict__ g_out, const unsigned* __restrict__ scale_buf,
-                    const uint8_t* __restrict__ fstash, uint8_t* __restrict__ gstash, float* __restrict__ g_x,
-                    const float* __restrict__ ray_batch, int ray_stride, const float* __restrict__ z, int64_t M,
-                    int S, int L_pts, FwdPlan P, BwdPlan B) {
+__global__ void __launch_bounds__(CH_THREADS, 1)
+mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ g_out,
+                    const unsigned* __restrict__ scale_buf, const uint8_t* __restrict__ fstash,
+                    uint8_t* __restrict__ gstash, uint8_t* __restrict__ genc, int64_t M, ChainPlan C, FwdPlan P,
+                    BwdPlan Bp) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], a_ready[2], d_ready[2];
+  __shared__ ChainBars B;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + TROWS - 1) / TROWS;
-  const int64_t nsuper = (ntiles + 1) / 2;
-  float* sparams = reinterpret_cast<float*>(smem + DgSmem::PARAMS);
-  for (int i = tid; i < TW + 384; i += BWD_THREADS) sparams[i] = head_params[P.w_alpha_off + i];
-  if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&a_ready[t], 128); mbar_init(&d_ready[t], 1); }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  // second 8-column group of both G16 tiles stays zero
+  for (int i = tid; i < 2 * CH_X16_BYTES / 16; i += CH_THREADS)
+    *reinterpret_cast<uint4*>(smem + DgSmem::G16 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) chain_init_bars(B);
+  if (warp == CH_WARP_MMA0) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(bstream);
-        for (int s = 0; s < B.nsteps; ++s) {
-          const uint32_t bytes = (uint32_t)B.steps[s].N * KS * 2;
-          for (int j = 0; j < B.steps[s].nslices; ++j) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], bytes);
-            bulk_g2s(smem + DgSmem::STAGE0 + stage * STAGE_BYTES, src, bytes, &full_bar[stage]);
-            src += bytes;
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
+  if (warp == CH_WARP_PRODUCER) {
+    if (lane == 0) chain_producer(B, smem, bstream, C, ntiles);
+  } else if (warp >= CH_WARP_MMA0) {
+    const ChainMap map = {0u, 0u, 0u, (uint32_t)DgSmem::G16, (uint32_t)CH_X16_BYTES};
+    chain_mma_issuer(B, smem, tmem_base, C, map, ntiles, (uint32_t)(warp - CH_WARP_MMA0));
+  } else if (warp < CH_WG_EPI0) {
+    // =========================== prologue warpgroup: loss-scaled head gradients of the NEXT tile ===========
+    const int row = tid - CH_WG_PRO * 32;
+    const float scale = grad_scale_from(scale_buf);
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = (int)(it & 1);
+      const int64_t m = tile * TROWS + row;
+      const float4 g = (m < M) ? reinterpret_cast<const float4*>(g_out)[m] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (it >= 2) mbar_wait(&B.pro_free[b], (uint32_t)(((it >> 1) + 1) & 1));
+      *reinterpret_cast<uint4*>(smem + DgSmem::G16 + b * CH_X16_BYTES + row * 16) =
+          make_uint4(pack_h2(g.x * scale, g.y * scale), pack_h2(g.z * scale, g.w * scale), 0u, 0u);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B.pro_ready[b]);
     }
-  } else if (warp == 1 || warp == 2) {
-    if (lane == 0) {   // MMA issuers: warp 1 -> tile slot 0, warp 2 -> tile slot 1
-      const int t = warp - 1;
-      int stage = 0; uint32_t phase = 0, a_phase = 0;
-      const uint32_t sbase = smem_u32(smem);
-      const uint32_t tacc = tmem_base + t * 256;
-      const uint32_t a_hi = desc_hi(128u), b_hi = desc_hi(128u);
-      const uint32_t g_lo = desc_lo(sbase + DgSmem::G0 + t * H_BYTES, TROWS * 16u);
-      constexpr uint32_t A_K16 = (2u * TROWS * 16u) >> 4;
-      for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
-        const bool active = (2 * st + t) < ntiles;
-        for (int s = 0; s < B.nsteps; ++s) {
-          const int N = B.steps[s].N, ns = B.steps[s].nslices;
-          const uint32_t idesc = make_idesc_f16(TROWS, N, 0, 0);
-          const uint32_t b_lbo = (uint32_t)N * 16u;
-          const uint32_t B_K16 = (2u * b_lbo) >> 4;
-          for (int j = 0; j < ns; ++j) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            if (active) {
-              if (j == 0) { mbar_wait(&a_ready[t], a_phase); a_phase ^= 1; tc_fence_after(); }
-              const uint32_t b_lo = desc_lo(sbase + DgSmem::STAGE0 + stage * STAGE_BYTES, b_lbo);
-              const uint32_t a_lo = g_lo + (uint32_t)(2 * j) * A_K16;
-              umma_f16_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, j > 0 ? 1u : 0u);
-              umma_f16_lohi(tacc, a_lo + A_K16, a_hi, b_lo + B_K16, b_hi, idesc, 1u);
-              umma_commit(&empty_bar[stage]);
-            } else {
-              mbar_arrive(&empty_bar[stage]);
-            }
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-          }
-          if (active) umma_commit(&d_ready[t]);
-        }
-      }
-    }
-  } else {
-    const int t = (warp - EPI_WARP0) >> 2;
+  } else if (warp < CH_WARP_PRODUCER) {
+    // =========================== epilogue warpgroups ===========================
+    const int g = (warp - CH_WG_EPI0) >> 2;
     const int row = 32 * (warp & 3) + lane;
     const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
-    uint8_t* Gb = smem + DgSmem::G0 + t * H_BYTES;
-    uint8_t* Eb = smem + DgSmem::ENC0 + t * ENC_BYTES;
-    const bool leader = ((warp - EPI_WARP0) & 3) == 0 && lane == 0;
-    const int bar_id = 1 + t;
-    const float scale = grad_scale_from(scale_buf);
-    const float inv_scale = 1.f / scale;
-    const float* wa = sparams;
-    const float* wr = sparams + TW;
-    uint32_t d_phase = 0;
-    for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
-      const int64_t tile = 2 * st + t;
-      if (tile >= ntiles) continue;
-      const int64_t m = tile * TROWS + row;
-      const bool valid = m < M;
+    uint8_t* act = smem + ChSmem::ACT;
+    uint32_t d_phase = 0, acc_sel = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const uint8_t* frec = fstash + tile * (int64_t)P.rec_bytes;
-      uint8_t* grec = gstash + tile * (int64_t)B.grec_bytes;
-      // ---- prologue: dZ of the views layer from g_out (rgb head backward + ReLU mask)
-      float4 g = valid ? reinterpret_cast<const float4*>(g_out)[m] : make_float4(0.f, 0.f, 0.f, 0.f);
-      g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
-      const float g_sigma = g.w;
-      {
-        const uint4 mv = *reinterpret_cast<const uint4*>(frec + P.rec_maskv + row * 16);
-        const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-        if (leader) bulk_wait_read_all();
-        named_bar_sync(bar_id, 128);
-#pragma unroll 4
-        for (int gq = 0; gq < 16; ++gq) {
-          float v[8];
+      uint8_t* grec = gstash + tile * (int64_t)Bp.grec_bytes;
+      for (int s = 0; s < C.nsteps; ++s, acc_sel ^= 1u) {
+        const ChainStep S_ = C.steps[s];
+        const int nround = S_.N >> 6;
+        // the ReLU bits of my columns (one word per round), fetched before waiting on the MMA
+        uint32_t mw[4] = {0u, 0u, 0u, 0u};
+        if (S_.epi == BE_TRUNK) {
+          const uint32_t* mp = reinterpret_cast<const uint32_t*>(frec + P.rec_mask + (S_.p0 * TROWS + row) * 32);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int j = gq * 8 + i;
-            float x = g.x * wr[j] + g.y * wr[128 + j] + g.z * wr[256 + j];
-            v[i] = relu_mask_test(mw[j >> 5], j & 31) ? 0.f : x;   // stash bit = 1: unit was inactive
-          }
-          uint4 q;
-          q.x = pack_h2(v[0], v[1]); q.y = pack_h2(v[2], v[3]); q.z = pack_h2(v[4], v[5]); q.w = pack_h2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(Gb + gq * (TROWS * 16) + row * 16) = q;
+          for (int rd = 0; rd < 4; ++rd) mw[rd] = mp[2 * rd + g];
+        } else if (S_.epi == BE_VIEWS) {
+          const uint32_t* mp = reinterpret_cast<const uint32_t*>(frec + P.rec_maskv + row * 16);
+          mw[0] = mp[g]; mw[1] = mp[2 + g];
         }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&a_ready[t]);
-      named_bar_sync(bar_id, 128);
-      if (leader) { bulk_s2g(grec + B.grec_v, Gb, HV_BYTES); bulk_commit(); }
-
-      for (int s = 0; s < B.nsteps; ++s) {
-        const BwdStep& S_ = B.steps[s];
-        const bool last = (s == B.nsteps - 1);
-        uint32_t mw[8];
-        if (S_.epi == BEPI_TRUNK) {   // prefetch the 256 ReLU bits of this row before waiting on the MMA
-          const uint4* mp = reinterpret_cast<const uint4*>(frec + P.rec_mask + (S_.mask_layer * TROWS + row) * 32);
-          const uint4 m0 = mp[0], m1 = mp[1];
-          mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w; mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
-        }
-        mbar_wait(&d_ready[t], d_phase); d_phase ^= 1;
+        mbar_wait(&B.d_ready[acc_sel], (d_phase >> acc_sel) & 1u); d_phase ^= (1u << acc_sel);
         tc_fence_after();
-        if (S_.epi == BEPI_FEAT || S_.epi == BEPI_TRUNK) {
-          const uint32_t tacc = tmem_base + tlane + t * 256;
-          uint32_t ra[32], rb2[32];
-          tmem_ld32(tacc, ra);                  // overlaps with the wait on the previous dZ store
-          if (leader) bulk_wait_read_all();   // the previous dZ blob is still being stored from Gb
-          named_bar_sync(bar_id, 128);
+        const uint32_t tacc = tmem_base + tlane + acc_sel * 256u + 32u * g;
+        uint32_t ra[32], rb2[32], pw[16];
+        tmem_ld32(tacc, ra);
+#pragma unroll 1
+        for (int rd2 = 0; rd2 < nround; rd2 += 2) {
 #pragma unroll
-          for (int cc = 0; cc < TW; cc += 64) {
-#pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
+          for (int hb = 0; hb < 2; ++hb) {
+            const int rd = rd2 + hb;
+            if (rd < nround) {
               uint32_t (&r)[32] = hb ? rb2 : ra;
-              const int c = cc + 32 * hb;
+              const int col = 64 * rd + 32 * g;
               tmem_ld_wait();
-              if (c + 32 < TW) tmem_ld32(tacc + c + 32, hb ? ra : rb2);
-              if (S_.add_alpha) {               // + g_sigma * w_alpha: gradient arriving through the sigma head
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 w4 = reinterpret_cast<const float4*>(wa)[(c >> 2) + j4];
-                  r[4 * j4 + 0] = __float_as_uint(fmaf(g_sigma, w4.x, __uint_as_float(r[4 * j4 + 0])));
-                  r[4 * j4 + 1] = __float_as_uint(fmaf(g_sigma, w4.y, __uint_as_float(r[4 * j4 + 1])));
-                  r[4 * j4 + 2] = __float_as_uint(fmaf(g_sigma, w4.z, __uint_as_float(r[4 * j4 + 2])));
-                  r[4 * j4 + 3] = __float_as_uint(fmaf(g_sigma, w4.w, __uint_as_float(r[4 * j4 + 3])));
-                }
-              }
-              uint32_t pw[16];
-#pragma unroll
-              for (int w = 0; w < 16; ++w) pw[w] = pack_h2(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]));
-              if (S_.epi == BEPI_TRUNK) {       // ReLU gate of the producing layer: 1.25 integer ops per element
-                const uint32_t m = mw[c >> 5];
+              if (rd + 1 < nround) tmem_ld32(tacc + 64u * (rd + 1), hb ? ra : rb2);
+              else chain_release_acc(B, (int)acc_sel, lane);
+              pack_chunk<false>(r, pw);
+              if (S_.epi == BE_TRUNK || S_.epi == BE_VIEWS) {   // ReLU gate of the producing layer
+                const uint32_t m = mw[rd];
                 pw[0] = relu_mask_apply<0>(pw[0], m);   pw[1] = relu_mask_apply<1>(pw[1], m);
                 pw[2] = relu_mask_apply<2>(pw[2], m);   pw[3] = relu_mask_apply<3>(pw[3], m);
                 pw[4] = relu_mask_apply<4>(pw[4], m);   pw[5] = relu_mask_apply<5>(pw[5], m);
@@ -315,90 +239,76 @@ mlp_tc_dgrad_kernel(const __half* __restrict__ bstream, const float* __restrict_
                 pw[12] = relu_mask_apply<12>(pw[12], m); pw[13] = relu_mask_apply<13>(pw[13], m);
                 pw[14] = relu_mask_apply<14>(pw[14], m); pw[15] = relu_mask_apply<15>(pw[15], m);
               }
+              if (S_.epi != BE_ENC) {
+                if (S_.writes_a) {
 #pragma unroll
-              for (int gq = 0; gq < 4; ++gq)
-                *reinterpret_cast<uint4*>(Gb + ((c >> 3) + gq) * (TROWS * 16) + row * 16) =
-                    make_uint4(pw[4 * gq], pw[4 * gq + 1], pw[4 * gq + 2], pw[4 * gq + 3]);
-            }
-          }
-          fence_proxy_async();
-          tc_fence_before();
-          if (!last) mbar_arrive(&a_ready[t]);
-          named_bar_sync(bar_id, 128);
-          if (leader) { bulk_s2g(grec + S_.dz_off, Gb, H_BYTES); bulk_commit(); }
-        } else if (S_.epi == BEPI_ENC_SAVE) {
-#pragma unroll 1
-          for (int cc = 0; cc < 64; cc += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + tlane + t * 256 + cc, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              uint4 q;
-              q.x = pack_h2(__uint_as_float(r[8 * gq + 0]), __uint_as_float(r[8 * gq + 1]));
-              q.y = pack_h2(__uint_as_float(r[8 * gq + 2]), __uint_as_float(r[8 * gq + 3]));
-              q.z = pack_h2(__uint_as_float(r[8 * gq + 4]), __uint_as_float(r[8 * gq + 5]));
-              q.w = pack_h2(__uint_as_float(r[8 * gq + 6]), __uint_as_float(r[8 * gq + 7]));
-              *reinterpret_cast<uint4*>(Eb + ((cc >> 3) + gq) * (TROWS * 16) + row * 16) = q;
-            }
-          }
-          tc_fence_before();
-          mbar_arrive(&a_ready[t]);   // the A operand (Gb) is unchanged; the accumulator columns are free again
-        } else {  // BEPI_ENC_FINAL: d/d(gamma(x)) -> d/dx through the encoder
-          float ge[64];
-#pragma unroll
-          for (int cc = 0; cc < 64; cc += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + tlane + t * 256 + cc, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) ge[cc + j] = __uint_as_float(r[j]);
-          }
-          if (B.has_skip_enc) {
-#pragma unroll
-            for (int gq = 0; gq < 8; ++gq) {
-              float v[8];
-              unpack8(*reinterpret_cast<const uint4*>(Eb + gq * (TROWS * 16) + row * 16), v);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) ge[gq * 8 + i] += v[i];
-            }
-          }
-          if (valid && g_x != nullptr) {
-            const int64_t rr = m / S;
-            const float* rb = ray_batch + rr * ray_stride;
-            const float zz = z[m];
-            float x[3];
-            x[0] = __fadd_rn(rb[0], __fmul_rn(rb[3], zz));
-            x[1] = __fadd_rn(rb[1], __fmul_rn(rb[4], zz));
-            x[2] = __fadd_rn(rb[2], __fmul_rn(rb[5], zz));
-            float gx[3] = {ge[0], ge[1], ge[2]};
-            float f = 1.f;
-#pragma unroll
-            for (int l = 0; l < 10; ++l) {
-              if (l < L_pts) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  float sn, cs;
-                  sincosf(x[c] * f, &sn, &cs);
-                  gx[c] += f * (cs * ge[3 + 6 * l + c] - sn * ge[3 + 6 * l + 3 + c]);
+                  for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(act + ((col >> 3) + q) * (TROWS * 16) + row * 16) =
+                        make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
+                  chain_publish(B, rd, lane);
                 }
+                store_chunk_global(grec + S_.off0, col, row, pw);
+              } else {
+                store_chunk_global(genc + (tile * 2 + S_.p0) * (int64_t)ENC_BYTES, col, row, pw);
               }
-              f *= 2.f;
             }
-            g_x[m * 3 + 0] = gx[0] * inv_scale;
-            g_x[m * 3 + 1] = gx[1] * inv_scale;
-            g_x[m * 3 + 2] = gx[2] * inv_scale;
           }
-          tc_fence_before();
-          if (!last) mbar_arrive(&a_ready[t]);
+        }
+        if (S_.writes_a && nround < 4) {     // a 128-wide output: groups 2 and 3 do not exist, complete them empty
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(&B.a_ready[2]); mbar_arrive(&B.a_ready[3]); }
         }
       }
     }
-    if (leader) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == CH_WARP_MMA0) tmem_dealloc(tmem_base, 512);
+}
+
+// d/dx of the positional encoder from the two d/d gamma(x) blobs (loss-scaled fp16):  one thread per sample
+__global__ void __launch_bounds__(128)
+enc_bwd_kernel(const uint8_t* __restrict__ genc, const float* __restrict__ ray_batch, int ray_stride,
+               const float* __restrict__ z, const unsigned* __restrict__ scale_buf, float* __restrict__ g_x,
+               int64_t M, int S, int L_pts) {
+  const int64_t tile = blockIdx.x;
+  const int row = threadIdx.x;
+  const int64_t m = tile * TROWS + row;
+  if (m >= M) return;
+  const float inv_scale = 1.f / grad_scale_from(scale_buf);
+  float ge[64];
+#pragma unroll
+  for (int gq = 0; gq < 8; ++gq) {
+    float v0[8], v1[8];
+    unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 0) * (int64_t)ENC_BYTES + gq * (TROWS * 16) + row * 16), v0);
+    unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 1) * (int64_t)ENC_BYTES + gq * (TROWS * 16) + row * 16), v1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ge[gq * 8 + i] = v0[i] + v1[i];
+  }
+  const int64_t rr = m / S;
+  const float* rb = ray_batch + rr * ray_stride;
+  const float zz = z[m];
+  float x[3];
+  x[0] = __fadd_rn(rb[0], __fmul_rn(rb[3], zz));
+  x[1] = __fadd_rn(rb[1], __fmul_rn(rb[4], zz));
+  x[2] = __fadd_rn(rb[2], __fmul_rn(rb[5], zz));
+  float gx[3] = {ge[0], ge[1], ge[2]};
+  float f = 1.f;
+#pragma unroll
+  for (int l = 0; l < 10; ++l) {
+    if (l < L_pts) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float sn, cs;
+        sincosf(x[c] * f, &sn, &cs);
+        gx[c] += f * (cs * ge[3 + 6 * l + c] - sn * ge[3 + 6 * l + 3 + c]);
+      }
+    }
+    f *= 2.f;
+  }
+  g_x[m * 3 + 0] = gx[0] * inv_scale;
+  g_x[m * 3 + 1] = gx[1] * inv_scale;
+  g_x[m * 3 + 2] = gx[2] * inv_scale;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -766,18 +676,19 @@ int lush_tc_gather_head_params(const MlpLayout& L, const float* params, float* d
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct BwdWorkspace {
-  size_t bstream, head, scale, gx, gstash, total;
+  size_t bstream, head, scale, gx, genc, gstash, total;
 };
 static BwdWorkspace bwd_ws_layout(const MlpLayout& L, int64_t M, bool need_in) {
   FwdPlan P; make_fwd_plan(L, P);
-  BwdPlan B; BPackPlan K; make_bwd_plan(L, need_in, B, K);
+  ChainPlan C; BwdPlan B; BPackPlan K; make_bwd_chain(L, need_in, C, B, K);
   const int64_t ntiles = (M + TROWS - 1) / TROWS;
   BwdWorkspace w;
   size_t off = 0;
-  w.bstream = off; off = align256(off + (size_t)B.bstream_bytes);
+  w.bstream = off; off = align256(off + (size_t)C.stream_bytes);
   w.head = off; off = align256(off + (size_t)P.nparam_floats * 4);
   w.scale = off; off = align256(off + 256);
   w.gx = off; off = align256(off + (size_t)M * 3 * 4);
+  w.genc = off; off = align256(off + (size_t)ntiles * 2 * ENC_BYTES);
   w.gstash = off; off = align256(off + (size_t)ntiles * B.grec_bytes);
   w.total = off;
   return w;
@@ -793,7 +704,7 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
   const int64_t M = R * S;
   const bool need_in = g_ray_batch != nullptr;
   FwdPlan P; make_fwd_plan(L, P);
-  BwdPlan B; BPackPlan K; make_bwd_plan(L, need_in, B, K);
+  ChainPlan C; BwdPlan B; BPackPlan K; make_bwd_chain(L, need_in, C, B, K);
   const BwdWorkspace w = bwd_ws_layout(L, M, true);
   if (!workspace || workspace_bytes < w.total) {
     set_error("mlp_bwd(tc): workspace too small (%zu < %zu)", workspace_bytes, w.total);
@@ -806,9 +717,10 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
   float* head = reinterpret_cast<float*>(ws + w.head);
   unsigned* scale_buf = reinterpret_cast<unsigned*>(ws + w.scale);
   float* gx = reinterpret_cast<float*>(ws + w.gx);
+  uint8_t* genc = ws + w.genc;
   uint8_t* gstash = ws + w.gstash;
   const uint8_t* fstash = reinterpret_cast<const uint8_t*>(stash);
-  const int64_t ntiles = (M + TROWS - 1) / TROWS, nsuper = (ntiles + 1) / 2;
+  const int64_t ntiles = (M + TROWS - 1) / TROWS;
 
   int rc = check_cuda(cudaMemsetAsync(scale_buf, 0, 256, st), "mlp_bwd(tc): memset");
   if (rc) return rc;
@@ -823,10 +735,9 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
     rc = check_cuda(cudaFuncSetAttribute(mlp_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                     "mlp_bwd(tc): dgrad smem attr");
     if (rc) return rc;
-    int grid = (int)(nsuper < kNumSMs ? nsuper : kNumSMs);
-    mlp_tc_dgrad_kernel<<<grid, BWD_THREADS, smem, st>>>(bstream, head, g_out, scale_buf, fstash, gstash,
-                                                        need_in ? gx : nullptr, ray_batch, ray_stride, z, M, S,
-                                                        desc->L_pts, P, B);
+    int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    mlp_tc_dgrad_kernel<<<grid, CH_THREADS, smem, st>>>((const uint8_t*)bstream, g_out, scale_buf, fstash, gstash, genc,
+                                                       M, C, P, B);
     LUSH_LAUNCH_CHECK("mlp_tc_dgrad");
   }
   {
@@ -850,6 +761,8 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
     LUSH_LAUNCH_CHECK("head_grads");
   }
   if (need_in) {
+    enc_bwd_kernel<<<(unsigned)ntiles, 128, 0, st>>>(genc, ray_batch, ray_stride, z, scale_buf, gx, M, S, desc->L_pts);
+    LUSH_LAUNCH_CHECK("enc_bwd");
     ray_grad_reduce_kernel<<<(unsigned)((R + 3) / 4), 128, 0, st>>>(gx, z, gstash, B.grec_bytes, B.grec_v, params,
                                                                    L.views_w, L.W + L.in_ch_v, L.in_ch_v,
                                                                    desc->L_views, ray_batch, ray_stride, scale_buf,

@@ -163,7 +163,7 @@ __device__ __forceinline__ void encode_row(uint8_t* blob, uint8_t* gdst, int row
     q.z = pack_h2(vals[8 * g + 4], vals[8 * g + 5]);
     q.w = pack_h2(vals[8 * g + 6], vals[8 * g + 7]);
     *reinterpret_cast<uint4*>(blob + g * (TROWS * 16) + row * 16) = q;
-    if (gdst) *reinterpret_cast<uint4*>(gdst + g * (TROWS * 16) + row * 16) = q;
+    if (gdst) *reinterpret_cast<uint4*>(gdst + stash_off(NCOL / 8, row, g)) = q;
   }
 }
 
@@ -295,7 +295,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
               chain_publish(B, rd, lane);
               if (tracer && rd < 2) chain_trace(C, it, s, 6 + 4 * g + rd);
-              if (TRAIN) store_chunk_global(rec + S_.off0, col, row, pw);
+              if (TRAIN) store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
             } else {
               // views layer: ReLU, rgb head partial sums over my columns; warpgroup 1 combines
 #pragma unroll
@@ -309,7 +309,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               }
               if (TRAIN) {
                 pack_chunk<true>(r, pw);
-                store_chunk_global(rec + S_.off0, col, row, pw);
+                store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
               }
             }
           }

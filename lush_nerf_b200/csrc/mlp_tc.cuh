@@ -145,11 +145,19 @@ __device__ __forceinline__ void pack_chunk(const uint32_t (&r)[32], uint32_t (&p
     pw[w] = RELU ? pack_h2_relu(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]))
                  : pack_h2(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]));
 }
-// 32 columns (4 groups of 8) of one row of a [128 x *] tile-canonical blob in global memory; c = first column
-__device__ __forceinline__ void store_chunk_global(uint8_t* blob, int c, int row, const uint32_t (&pw)[16]) {
+// ---- stash blobs in global memory (activations / gradients kept for the wgrad GEMM) ----------------------
+// A [128 x C] fp16 blob is stored as two 64-row halves, each half in the tile-canonical layout with 64 rows:
+//     offset(r, c) = (r/64) * (C/8 * 1024) + (c/8) * 1024 + (r%64) * 16 + (c%8) * 2
+// so that one 64-sample half of a blob is ONE contiguous run of bytes which is, verbatim, the MN-major UMMA
+// operand image the wgrad kernel wants in shared memory (a single bulk copy per operand and stage).
+__host__ __device__ constexpr uint32_t stash_off(uint32_t ncg, uint32_t r, uint32_t cg) {
+  return (r >> 6) * (ncg * 1024u) + cg * 1024u + (r & 63u) * 16u;
+}
+// 32 columns (4 groups of 8) of one row of a [128 x 8*ncg] stash blob; c = first column
+__device__ __forceinline__ void store_chunk_global(uint8_t* blob, int ncg, int c, int row, const uint32_t (&pw)[16]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g)
-    *reinterpret_cast<uint4*>(blob + ((c >> 3) + g) * (TROWS * 16) + row * 16) =
+    *reinterpret_cast<uint4*>(blob + stash_off(ncg, row, (c >> 3) + g)) =
         make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
 }
 

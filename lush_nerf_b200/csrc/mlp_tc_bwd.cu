@@ -247,9 +247,9 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
                         make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
                   chain_publish(B, rd, lane);
                 }
-                store_chunk_global(grec + S_.off0, col, row, pw);
+                store_chunk_global(grec + S_.off0, S_.N >> 3, col, row, pw);
               } else {
-                store_chunk_global(genc + (tile * 2 + S_.p0) * (int64_t)ENC_BYTES, col, row, pw);
+                store_chunk_global(genc + (tile * 2 + S_.p0) * (int64_t)ENC_BYTES, 8, col, row, pw);
               }
             }
           }
@@ -280,8 +280,8 @@ enc_bwd_kernel(const uint8_t* __restrict__ genc, const float* __restrict__ ray_b
 #pragma unroll
   for (int gq = 0; gq < 8; ++gq) {
     float v0[8], v1[8];
-    unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 0) * (int64_t)ENC_BYTES + gq * (TROWS * 16) + row * 16), v0);
-    unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 1) * (int64_t)ENC_BYTES + gq * (TROWS * 16) + row * 16), v1);
+    unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 0) * (int64_t)ENC_BYTES + stash_off(8, row, gq)), v0);
+    unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 1) * (int64_t)ENC_BYTES + stash_off(8, row, gq)), v1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) ge[gq * 8 + i] = v0[i] + v1[i];
   }
@@ -382,61 +382,58 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
   const int nunits = Wp.njobs * Wp.nchunks;
 
   if (warp == 0) {
-    // ---- producer: 1 KB bulk copies (64 rows of one 8-column group) issued by all 32 lanes
-    int stage = 0; uint32_t phase = 0;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-      const WJob& J = Wp.jobs[u / Wp.nchunks];
-      const int64_t t0 = (int64_t)(u % Wp.nchunks) * Wp.tiles_per_chunk;
-      const int64_t t1 = (t0 + Wp.tiles_per_chunk < ntiles) ? t0 + Wp.tiles_per_chunk : ntiles;
-      const int ga = J.nout / 8, gb = J.kin / 8;
-      for (int64_t tile = t0; tile < t1; ++tile) {
-        const uint8_t* asrc = gstash + tile * (int64_t)grec_bytes + J.dz_off;
-        const uint8_t* bsrc = fstash + tile * (int64_t)frec_bytes + J.x_off;
-        for (int half = 0; half < 2; ++half) {
-          if (lane == 0) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(ga + gb) * 1024u);
-          }
-          __syncwarp();
-          uint8_t* sa = smem + stage * WG_STAGE_BYTES;
-          uint8_t* sb = sa + 32768;
-          for (int gi = lane; gi < ga; gi += 32) bulk_g2s(sa + gi * 1024, asrc + gi * 2048 + half * 1024, 1024, &full_bar[stage]);
-          for (int gi = lane; gi < gb; gi += 32) bulk_g2s(sb + gi * 1024, bsrc + gi * 2048 + half * 1024, 1024, &full_bar[stage]);
-          if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
+    // ---- producer: a 64-sample half of a stash blob is one contiguous run (see stash_off) = the operand image
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0, free_phase = 0;
-      const uint32_t sbase = smem_u32(smem);
-      bool first_unit = true;
+      int stage = 0; uint32_t phase = 0;
       for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
         const WJob& J = Wp.jobs[u / Wp.nchunks];
         const int64_t t0 = (int64_t)(u % Wp.nchunks) * Wp.tiles_per_chunk;
         const int64_t t1 = (t0 + Wp.tiles_per_chunk < ntiles) ? t0 + Wp.tiles_per_chunk : ntiles;
-        const uint32_t idesc = make_idesc_f16(128, J.kin, 1, 1);
-        if (!first_unit) { mbar_wait(&acc_free, free_phase); free_phase ^= 1; tc_fence_after(); }
-        first_unit = false;
-        bool first = true;
-        for (int64_t it = 0; it < 2 * (t1 - t0); ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = sbase + stage * WG_STAGE_BYTES, sb = sa + 32768;
-          for (int h = 0; h < J.nout / 128; ++h) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = make_smem_desc(sa + h * 16 * 1024 + kk * 256, 128u, 1024u);
-              const uint64_t bd = make_smem_desc(sb + kk * 256, 128u, 1024u);
-              umma_f16(tmem_base + h * 256, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
-            }
+        const uint32_t abytes = (uint32_t)(J.nout / 8) * 1024u, bbytes = (uint32_t)(J.kin / 8) * 1024u;
+        for (int64_t tile = t0; tile < t1; ++tile) {
+          const uint8_t* asrc = gstash + tile * (int64_t)grec_bytes + J.dz_off;
+          const uint8_t* bsrc = fstash + tile * (int64_t)frec_bytes + J.x_off;
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], abytes + bbytes);
+            uint8_t* sa = smem + stage * WG_STAGE_BYTES;
+            bulk_g2s(sa, asrc + half * abytes, abytes, &full_bar[stage]);
+            bulk_g2s(sa + 32768, bsrc + half * bbytes, bbytes, &full_bar[stage]);
+            if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
           }
-          first = false;
-          umma_commit(&empty_bar[stage]);
-          if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_ready);
       }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (converged warp, one elected lane issues): per 64-sample stage 4 K=16 MMAs per output half,
+    // both operands MN-major views of the staged blobs (16 samples = 256 bytes further per MMA)
+    int stage = 0; uint32_t phase = 0, free_phase = 0;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t hi = desc_hi(1024u);
+    bool first_unit = true;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const WJob& J = Wp.jobs[u / Wp.nchunks];
+      const int64_t t0 = (int64_t)(u % Wp.nchunks) * Wp.tiles_per_chunk;
+      const int64_t t1 = (t0 + Wp.tiles_per_chunk < ntiles) ? t0 + Wp.tiles_per_chunk : ntiles;
+      const uint32_t idesc = make_idesc_f16(128, J.kin, 1, 1);
+      const int nhalf = J.nout / 128;
+      if (!first_unit) { mbar_wait(&acc_free, free_phase); free_phase ^= 1; }
+      first_unit = false;
+      uint32_t acc = 0;
+      for (int64_t it = 0; it < 2 * (t1 - t0); ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = desc_lo(sbase + stage * WG_STAGE_BYTES, 128u);
+          const uint32_t b_lo = desc_lo(sbase + stage * WG_STAGE_BYTES + 32768, 128u);
+          mma_ss<4>(tmem_base, a_lo, b_lo, hi, 16u, 16u, idesc, acc);
+          if (nhalf == 2) mma_ss<4>(tmem_base + 256u, a_lo + 1024u, b_lo, hi, 16u, 16u, idesc, acc);
+          umma_commit(&empty_bar[stage]);
+        }
+        acc = 1;
+        if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&acc_ready);
     }
   } else {
     // ---- epilogue warps: bias column sums from the dZ stage while the MMAs run, then the accumulator flush
@@ -464,13 +461,20 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
           for (int a = 0; a < 2; ++a) {
             const int gi = q + 16 * a;
             if (gi < ngrp) {
+              // 8 rows x 8 columns: partial sums of 8 values in packed fp16, then one conversion to fp32
+              uint4 acc4 = *reinterpret_cast<const uint4*>(sa + gi * 1024 + r8 * 16);
+              __half2* ah = reinterpret_cast<__half2*>(&acc4);
 #pragma unroll
-              for (int rr = 0; rr < 8; ++rr) {
-                float v[8];
-                unpack8(*reinterpret_cast<const uint4*>(sa + gi * 1024 + (r8 + 8 * rr) * 16), v);
+              for (int rr = 1; rr < 8; ++rr) {
+                const uint4 v4 = *reinterpret_cast<const uint4*>(sa + gi * 1024 + (r8 + 8 * rr) * 16);
+                const __half2* vh = reinterpret_cast<const __half2*>(&v4);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) bs[a][i] += v[i];
+                for (int i = 0; i < 4; ++i) ah[i] = __hadd2(ah[i], vh[i]);
               }
+              float v[8];
+              unpack8(acc4, v);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bs[a][i] += v[i];
             }
           }
         }
@@ -551,14 +555,14 @@ head_grads_kernel(const uint8_t* __restrict__ fstash, const float* __restrict__ 
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         float v[8];
-        unpack8(*reinterpret_cast<const uint4*>(rec + h_last_off + (w + 8 * a) * (TROWS * 16) + row * 16), v);
+        unpack8(*reinterpret_cast<const uint4*>(rec + h_last_off + stash_off(32, row, w + 8 * a)), v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) aa[a][i] = fmaf(g.w, v[i], aa[a][i]);
       }
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
         float v[8];
-        unpack8(*reinterpret_cast<const uint4*>(rec + hv_off + (w + 8 * a) * (TROWS * 16) + row * 16), v);
+        unpack8(*reinterpret_cast<const uint4*>(rec + hv_off + stash_off(16, row, w + 8 * a)), v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           ar[a][0][i] = fmaf(g.x, v[i], ar[a][0][i]);
@@ -628,7 +632,7 @@ ray_grad_reduce_kernel(const float* __restrict__ g_x, const float* __restrict__ 
       const int64_t tile = m / TROWS;
       const int row = (int)(m - tile * TROWS);
       float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(gstash + tile * (int64_t)grec_bytes + grec_v + gq * (TROWS * 16) + row * 16), v);
+      unpack8(*reinterpret_cast<const uint4*>(gstash + tile * (int64_t)grec_bytes + grec_v + stash_off(16, row, gq)), v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] += v[i];
     }

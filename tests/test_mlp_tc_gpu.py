@@ -206,3 +206,36 @@ def test_tc_training_step_vs_reference_golden(golden, det_state):
     gr = golden["fwd/rbk/g_rays"]
     assert ((rays.grad.cpu() - gr).norm() / gr.norm()).item() <= 1e-1
     print(f"tc training step: worst |grad| norm deviation vs reference {worst:.2e}")
+
+
+def test_tc_many_tiles_per_cta_forward_and_backward():
+    """Sizes with >10 tiles per persistent CTA (barrier-parity bookkeeping across tiles) and a ragged last tile."""
+    from oracle import lush_oracle as O
+    R, S = 1500, 127                                  # 1489 tiles of 128 samples on 148 CTAs, last tile partial
+    nets = O.det_nets()
+    shapes = O.mlp_param_shapes(8, 256, 63, 27, 4)
+    flat = torch.cat([nets["coarse"][n].reshape(-1) for n, _ in shapes]).cuda()
+    desc = _lib.MlpDesc(8, 256, 10, 4, 4, 0)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rb = torch.zeros(R, 11, device="cuda")
+    rb[:, :3] = torch.rand(R, 3, device="cuda", generator=g) * 2 - 1
+    rb[:, 3:6] = torch.randn(R, 3, device="cuda", generator=g) * 0.3
+    rb[:, 8:11] = torch.nn.functional.normalize(torch.randn(R, 3, device="cuda", generator=g), dim=-1)
+    z = torch.rand(R, S, device="cuda", generator=g).sort(-1)[0]
+    gout = torch.randn(R, S, 4, device="cuda", generator=g)
+    res = []
+    for impl in (0, 1):
+        views, off = [], 0
+        fl = flat.clone()
+        for _, shp in shapes:
+            n = int(np.prod(shp)); views.append(fl[off:off + n].view(shp).requires_grad_(True)); off += n
+        rbg = rb.clone().requires_grad_(True)
+        out = ops.mlp_apply(rbg, z, desc, impl, fl, views)
+        out.backward(gout)
+        res.append((out.detach(), [v.grad for v in views], rbg.grad))
+    scale = res[0][0].abs().amax().item()
+    assert (res[1][0] - res[0][0]).abs().max().item() / scale <= 4e-3
+    for (name, _), g1, g0 in zip(shapes, res[1][1], res[0][1]):
+        tol = 2e-3 if name.startswith(("alpha_linear", "rgb_linear")) else 8e-2
+        assert _rel(g1, g0) <= tol, (name, _rel(g1, g0))
+    assert _rel(res[1][2][:, 0:6], res[0][2][:, 0:6]) <= 8e-2

@@ -48,6 +48,18 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_traffic():
+    """dram bytes (read + write) of the scene-MLP kernels of ONE training step, from the committed ncu
+    `--set full` capture of this very command (profiles/r01_ncu_mlp_step.json, written by tools/ncu_step.py)."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_mlp_step.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return {"bytes_per_step": d["dram_bytes_per_step"], "source": "profiles/r01_ncu_mlp_step.json"}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -238,7 +250,11 @@ def main():
     launches = _lib.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    mlp_ms = sum(a.elapsed_time(b) for a, b in mlp_events)
+    def _ms(labels):
+        return sum(a.elapsed_time(b) for lab, a, b in mlp_events if lab in labels)
+    mlp_ms = _ms(("fwd", "bwd", "fwd_simt", "bwd_simt"))
+    fwd_ms, bwd_ms = _ms(("fwd",)), _ms(("bwd",))
+    simt_ms = _ms(("fwd_simt", "bwd_simt"))
     mlp_calls = len(mlp_events)
 
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step
@@ -271,6 +287,8 @@ def main():
             model(H, W, trainer.K, chunk=1024 * 32, poses=poses[:2], render_kwargs=dict(rk))   # warm-up frames
             torch.cuda.synchronize()
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            rsampler = ClockSampler(local)
+            rsampler.start()
             mlp_events.clear()
             ops.MLP_EVENT_SINK = mlp_events
             r0.record()
@@ -278,20 +296,37 @@ def main():
             r1.record()
             torch.cuda.synchronize()
             ops.MLP_EVENT_SINK = None
+        rclocks = rsampler.stop()
         ms_frame = r0.elapsed_time(r1) / args.render_frames
-        mlp_ms_frame = sum(a.elapsed_time(b) for a, b in mlp_events) / args.render_frames
+        mlp_ms_frame = sum(a.elapsed_time(b) for lab, a, b in mlp_events if lab == "fwd") / args.render_frames
         fl = FLOP_FWD_PER_SAMPLE * H * W * SAMPLES_PER_RAY
         render = {"ms_per_frame": ms_frame, "frames": args.render_frames, "rays_per_s": H * W / (ms_frame * 1e-3),
                   "image": f"{H}x{W}", "chunk": 32768, "mlp_ms_per_frame": mlp_ms_frame,
                   "mlp_tflops": fl / (mlp_ms_frame * 1e-3) / 1e12 if mlp_ms_frame > 0 else None,
-                  "finite": bool(torch.isfinite(rgbs).all().item())}
+                  "finite": bool(torch.isfinite(rgbs).all().item()), "clocks": rclocks}
         model.train()
 
     if rank == 0:
         peaks = measured_peaks()
         flops_step = 3 * FLOP_FWD_PER_SAMPLE * N_RAND * K_RAYS * SAMPLES_PER_RAY
-        achieved = (flops_step * args.steps / (mlp_ms * 1e-3)) / 1e12 if mlp_ms > 0 else None
+        tc = model.mlp_coarse.impl() == 1
+        scene_ms = (fwd_ms + bwd_ms) if tc else mlp_ms
+        achieved = (flops_step * args.steps / (scene_ms * 1e-3)) / 1e12 if scene_ms > 0 else None
         impl_name = {0: "fp32 SIMT (FFMA)", 1: "tcgen05 fp16 operands / fp32 accumulate"}[model.mlp_coarse.impl()]
+        # per launch class (CUDA events around the C-ABI calls on the launching stream, timed region only)
+        per_kernel = None
+        if tc and fwd_ms > 0 and bwd_ms > 0:
+            f = flops_step / 3 * args.steps
+            per_kernel = {
+                "mlp_fwd (pack + mlp_tc_fwd_kernel, stash written)": {
+                    "ms_per_step": fwd_ms / args.steps, "tflops": f / (fwd_ms * 1e-3) / 1e12,
+                    "frac_of_tensor_peak": f / (fwd_ms * 1e-3) / 1e12 / peaks["tflops"]},
+                "mlp_bwd (dgrad chain + wgrad GEMM + head/ray reductions)": {
+                    "ms_per_step": bwd_ms / args.steps, "tflops": 2 * f / (bwd_ms * 1e-3) / 1e12,
+                    "frac_of_tensor_peak": 2 * f / (bwd_ms * 1e-3) / 1e12 / peaks["tflops"]},
+                "noise MLP (fp32 SIMT, 4x128, 1024 rows)": {"ms_per_step": simt_ms / args.steps},
+            }
+        traffic = load_traffic()
         line = {
             "metric": "train rays/s (coarse+fine fwd+bwd, 64+64 samples)", "value": value, "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -303,10 +338,13 @@ def main():
             "gpu_launches": int(launches),
             "pixels_per_s": value / K_RAYS,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / peaks["tflops"]) if achieved else None,
+                         "traffic": traffic.get("bytes_per_step") if traffic else None,
+                         "traffic_source": traffic.get("source") if traffic else None,
+                         "per_kernel": per_kernel,
                          "kernel": f"encoder+MLP fwd+bwd ({impl_name}), all launches of the step; algorithmic "
                                    f"{flops_step / 1e12:.3f} TFLOP/step (3 x 1 186 816 FLOP x 983 040 samples)",
-                         "mlp_ms_per_step": mlp_ms / args.steps, "mlp_calls_per_step": mlp_calls / args.steps,
+                         "mlp_ms_per_step": scene_ms / args.steps, "mlp_calls_per_step": mlp_calls / args.steps,
                          "peak_source": peaks["source"]},
             "final_loss": loss_host,
             "render": render,

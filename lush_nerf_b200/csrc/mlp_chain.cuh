@@ -77,7 +77,8 @@ struct ChainStep {
 
 struct ChainPlan {
   int nsteps;
-  int debug;              // experiments only (LUSH_CHAIN_DEBUG): bit 0 = do not stream weights (results are garbage)
+  int debug;              // LUSH_CHAIN_DEBUG: bit 0 = do not stream weights (timing experiments only, results are
+                          // garbage), bit 1 = record the timeline trace of CTA 0 (tools/trace_chain.py)
   int64_t stream_bytes;   // weight stream per tile
   ChainStep steps[CH_MAX_STEPS];
 };

@@ -227,8 +227,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
       if (it >= 2) mbar_wait(&B.pro_free[b], (uint32_t)(((it >> 1) + 1) & 1));
       encode_row<32>(smem + FwdSmem::ENCV + b * ENCV_BYTES, TRAIN ? rec + P.rec_encv : nullptr, row, vx, vy, vz, L_views);
       if (it >= 1) mbar_wait(&B.enc_free, (uint32_t)((it + 1) & 1));
-      if (!(C.debug & 8) || it < 1)
-        encode_row<64>(smem + FwdSmem::ENC, TRAIN ? rec + P.rec_encp : nullptr, row, x0, x1, x2, L_pts);
+      encode_row<64>(smem + FwdSmem::ENC, TRAIN ? rec + P.rec_encp : nullptr, row, x0, x1, x2, L_pts);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.pro_ready[b]);

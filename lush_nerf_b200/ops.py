@@ -179,6 +179,11 @@ MLP_EVENT_SINK = None
 
 
 class _Timed:
+    """CUDA events around one C-ABI MLP call; appended to MLP_EVENT_SINK as (label, start, end) when it is a list."""
+
+    def __init__(self, label="mlp"):
+        self.label = label
+
     def __enter__(self):
         self.on = MLP_EVENT_SINK is not None
         if self.on:
@@ -189,7 +194,7 @@ class _Timed:
     def __exit__(self, *exc):
         if self.on:
             self.b.record()
-            MLP_EVENT_SINK.append((self.a, self.b))
+            MLP_EVENT_SINK.append((self.label, self.a, self.b))
 
 
 def mlp_impl_supported(desc: MlpDesc, impl: int, training: bool = False) -> bool:
@@ -216,7 +221,7 @@ class _MLP(torch.autograd.Function):
             stash = torch.empty((nb + 3) // 4, dtype=torch.float32, device=rb.device)
         wb = L.lush_mlp_workspace_bytes(byref(desc), R, S, impl, 0)
         ws = torch.empty((wb + 3) // 4, dtype=torch.float32, device=rb.device) if wb else None
-        with _Timed():
+        with _Timed("fwd" if impl == 1 else "fwd_simt"):
             check(L.lush_mlp_fwd(byref(desc), ptr(flat, "params"), ptr(rb, "ray_batch"), rb.shape[1], ptr(z, "z"),
                                  ptr(out), ptr(stash), ptr(ws), wb, R, S, impl, stream()), "lush_mlp_fwd")
         if training:
@@ -235,7 +240,7 @@ class _MLP(torch.autograd.Function):
         g_rb = _empty((R, 11), rb) if ctx.needs_input_grad[0] else None
         wb = L.lush_mlp_workspace_bytes(byref(desc), R, S, impl, 1)
         ws = torch.empty((wb + 3) // 4, dtype=torch.float32, device=rb.device) if wb else None
-        with _Timed():
+        with _Timed("bwd" if impl == 1 else "bwd_simt"):
             check(L.lush_mlp_bwd(byref(desc), ptr(flat), ptr(rb), rb.shape[1], ptr(z), ptr(g_out), ptr(stash),
                                  ptr(g_flat), ptr(g_rb), ptr(ws), wb, R, S, impl, stream()), "lush_mlp_bwd")
         grads, off = [], 0

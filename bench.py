@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "simt", "tc"], help="override LUSH_MLP_IMPL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the training step in a CUDA graph")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--render-frames", type=int, default=5)
     args = ap.parse_args()
@@ -228,34 +229,51 @@ def main():
     mlp_events = []
     ops.MLP_EVENT_SINK = None
 
-    # ---- warm-up
+    # ---- warm-up (eager)
     for i in range(args.warmup):
         trainer.step(resident[i])
     barrier()
 
-    # ---- timed region 1: inputs resident in HBM
+    def timed_pass(with_events):
+        """K steps over batches already resident in HBM; returns device ms (CUDA events on the launching stream)."""
+        ops.MLP_EVENT_SINK = mlp_events if with_events else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            trainer.step(resident[args.warmup + i])
+        e1.record()
+        barrier()
+        ops.MLP_EVENT_SINK = None
+        return e0.elapsed_time(e1)
+
+    # ---- timed region 1a: eager launches with CUDA events around every MLP call (roofline numerators, launch count)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    ops.MLP_EVENT_SINK = mlp_events
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        trainer.step(resident[args.warmup + i])
-    e1.record()
-    barrier()
-    ops.MLP_EVENT_SINK = None
+    ms_eager = timed_pass(True)
     launches = _lib.launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     def _ms(labels):
         return sum(a.elapsed_time(b) for lab, a, b in mlp_events if lab in labels)
     mlp_ms = _ms(("fwd", "bwd", "fwd_simt", "bwd_simt"))
     fwd_ms, bwd_ms = _ms(("fwd",)), _ms(("bwd",))
     simt_ms = _ms(("fwd_simt", "bwd_simt"))
     mlp_calls = len(mlp_events)
+
+    # ---- timed region 1b: the same step captured in ONE CUDA graph (Trainer.enable_cuda_graph) -- the product path
+    graphed = False
+    if not args.no_graph:
+        try:
+            graphed = bool(trainer.enable_cuda_graph(resident[0]))
+            for i in range(args.warmup):
+                trainer.step(resident[i])
+        except Exception as e:   # report, never hide: the eager path is the same kernels, only launched one by one
+            print(f"[bench] CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}", file=sys.stderr)
+            graphed = False
+            trainer._graph = None
+    ms_total = timed_pass(False) if graphed else ms_eager
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step
     barrier()
@@ -336,6 +354,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
+            "cuda_graph": graphed, "ms_per_step_eager": ms_eager / args.steps,
             "pixels_per_s": value / K_RAYS,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tflops"]) if achieved else None,

@@ -76,15 +76,16 @@ class Trainer:
         kw = dict(lr=lrate)
         if fused_adam and params[0].is_cuda:
             kw["fused"] = True
+            kw["capturable"] = True          # step counters live on the device: the step can be graph-captured
         # two parameter groups like the reference (run_lushnerf.py:359-371)
         self.optimizer = torch.optim.Adam([{"params": base}, {"params": noise, "lr": lrate}], **kw)
         self.allreduce = FlatGradAllReduce(params, group)
         self.render_kwargs = render_kwargs or {}
         self.lrate, self.global_step = lrate, 0
+        self._graph, self._static, self._static_loss = None, None, None
 
-    def step(self, batch, force_naive=False, allkernel=True, chunk=1024 * 32):
+    def _step_body(self, batch, force_naive=False, allkernel=True, chunk=1024 * 32):
         m = self.model
-        m.train()
         out = m(self.H, self.W, self.K, chunk=chunk, rays=batch["rays"],
                 rays_info={"images_idx": batch["images_idx"]}, retraw=True, force_naive=force_naive,
                 allkernel=allkernel, kernel_pixel=batch["fq_mask"], **self.render_kwargs)
@@ -93,8 +94,56 @@ class Trainer:
         loss.backward()
         self.allreduce()
         self.optimizer.step()
+        return loss
+
+    def step(self, batch, force_naive=False, allkernel=True, chunk=1024 * 32):
+        self.model.train()
+        if self._graph is not None and not force_naive and allkernel:
+            for k, v in self._static.items():       # H2D (or D2D) into the captured input buffers
+                v.copy_(batch[k], non_blocking=True)
+            self._graph.replay()
+            self.global_step += 1
+            return self._static_loss
+        loss = self._step_body(batch, force_naive, allkernel, chunk)
         self.global_step += 1
         return loss
+
+    def enable_cuda_graph(self, sample_batch, warmup=3):
+        """Capture one whole training step (forward, loss, backward, gradient all-reduce, Adam) in a CUDA graph:
+        ~240 launches become one graph launch.  The batch is copied into static buffers before every replay;
+        random draws (stratified jitter, sigma noise) come from the graph-registered default CUDA generator.
+        The NaN/Inf guard of the model runs in deferred mode (flag word inspected by `check_numerics()`)."""
+        import os
+        if self._graph is not None:
+            return True
+        dev = sample_batch["rays"].device
+        os.environ["LUSH_NUMERIC_GUARD"] = "off"    # no event queries / host copies inside the captured region
+        self._static = {k: v.to(dev).clone() for k, v in sample_batch.items()}
+        self.model.train()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_body(self._static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._static_loss = self._step_body(self._static)
+        self._graph = g
+        self.global_step += warmup
+        return True
+
+    def check_numerics(self):
+        """Deferred NaN/Inf guard for graph mode: one device->host read of the model's flag word."""
+        f = getattr(self.model, "_flags", None)
+        if f is not None:
+            bits = int(f.item())
+            f.zero_()
+            if bits:
+                self.model._print_flags(bits)
+            return bits
+        return 0
 
     def set_lr(self, decay_steps=250000, decay_rate=0.1):
         lr = self.lrate * (decay_rate ** (self.global_step / decay_steps))  # reference :681-685

@@ -273,19 +273,8 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               chain_release_acc(B, (int)acc_sel, lane);
               if (tracer) chain_trace(C, it, s, 5 + 4 * g);
             }
-            if (TRAIN && S_.epi != FE_FEATURE)
-              *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (col >> 5) * 4) = sign_bits(r);
-            if (S_.epi == FE_TRUNK_LAST) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 w4 = wa4[(col >> 2) + j4];
-                alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), w4.x, alpha);
-                alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f), w4.y, alpha);
-                alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), w4.z, alpha);
-                alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f), w4.w, alpha);
-              }
-            }
             if (S_.epi != FE_VIEWS) {
+              // critical path first: fp16 -> activation tile -> publish; everything else rides behind the hand-off
               if (S_.epi == FE_FEATURE) pack_chunk<false>(r, pw);
               else pack_chunk<true>(r, pw);
 #pragma unroll
@@ -294,7 +283,21 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
               chain_publish(B, rd, lane);
               if (tracer && rd < 2) chain_trace(C, it, s, 6 + 4 * g + rd);
-              if (TRAIN) store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
+              if (TRAIN) {
+                store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
+                if (S_.epi != FE_FEATURE)
+                  *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (col >> 5) * 4) = sign_bits(r);
+              }
+              if (S_.epi == FE_TRUNK_LAST) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 w4 = wa4[(col >> 2) + j4];
+                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), w4.x, alpha);
+                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f), w4.y, alpha);
+                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), w4.z, alpha);
+                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f), w4.w, alpha);
+                }
+              }
             } else {
               // views layer: ReLU, rgb head partial sums over my columns; warpgroup 1 combines
 #pragma unroll
@@ -309,6 +312,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               if (TRAIN) {
                 pack_chunk<true>(r, pw);
                 store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
+                *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (col >> 5) * 4) = sign_bits(r);
               }
             }
           }

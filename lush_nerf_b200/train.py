@@ -39,25 +39,19 @@ class FlatGradAllReduce:
     def __call__(self):
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
-        dev = self.params[0].device
-        if self.flat is None or self.flat.device != dev:
-            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:  # parameters without a gradient (NeRF_Noise.alpha_linear) contribute zeros
-            n = p.numel()
-            if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
+        # parameters without a gradient (NeRF_Noise.alpha_linear) contribute zeros and receive nothing back
+        with_grad = [p for p in self.params if p.grad is not None]
+        pieces = [p.grad.reshape(-1) if p.grad is not None else p.new_zeros(p.numel()) for p in self.params]
+        self.flat = torch.cat(pieces)                     # one multi-tensor pack kernel instead of one copy per tensor
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         self.flat.div_(dist.get_world_size(self.group))
-        off = 0
+        views, off = [], 0
         for p in self.params:
             n = p.numel()
             if p.grad is not None:
-                p.grad.copy_(self.flat[off:off + n].view_as(p.grad))
+                views.append(self.flat[off:off + n].view_as(p.grad))
             off += n
+        torch._foreach_copy_([p.grad for p in with_grad], views)   # one multi-tensor unpack kernel
 
 
 class Trainer:

@@ -60,6 +60,8 @@ __device__ __forceinline__ float ld_stream(const float* p) {
   return r;
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// 1/(1+exp(-x)): __frcp_rn is the correctly rounded reciprocal, i.e. bit-identical to the IEEE division 1.f/y
+// without the division routine's slow-path branches
+__device__ __forceinline__ float sigmoidf_(float x) { return __frcp_rn(1.f + expf(-x)); }
 
 }  // namespace lush

@@ -77,6 +77,11 @@ __device__ __forceinline__ float warp_excl_prod(float v, int lane, float& total)
   return lane == 0 ? 1.f : ex;
 }
 
+// 1 iff the exponent field of v is all ones (NaN or Inf): two integer instructions; the exact NaN/Inf split is
+// only computed for values that trip this test
+__device__ __forceinline__ unsigned nonfinite_bit(float v) {
+  return ((__float_as_uint(v) & 0x7fffffffu) + 0x00800000u) >> 31;
+}
 __device__ __forceinline__ int nanflag(float v) {
   return (isnan(v) ? 1 : 0) | (isinf(v) ? 2 : 0);
 }
@@ -123,8 +128,11 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
     if (valid) {
       if (weights) weights[r * S + i] = w;
       if (density && i + 1 < S) density[r * (S - 1) + i] = f.sigma;
-      fl |= (nanflag(c.rw.x) | nanflag(c.rw.y) | nanflag(c.rw.z) | nanflag(c.rw.w)) << 8;
-      if (i + 1 < S) fl |= nanflag(f.sigma) << 6;
+      if (nonfinite_bit(c.rw.x) | nonfinite_bit(c.rw.y) | nonfinite_bit(c.rw.z) | nonfinite_bit(c.rw.w) |
+          nonfinite_bit(f.sigma)) {   // rare
+        fl |= (nanflag(c.rw.x) | nanflag(c.rw.y) | nanflag(c.rw.z) | nanflag(c.rw.w)) << 8;
+        if (i + 1 < S) fl |= nanflag(f.sigma) << 6;
+      }
     }
   }
   sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);

@@ -177,8 +177,6 @@ def main():
     ap.add_argument("--mlp", default=None, choices=[None, "simt", "tc"], help="override LUSH_MLP_IMPL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the training step in a CUDA graph")
-    ap.add_argument("--graph-dist", action="store_true",
-                    help="also capture the step (with its NCCL all-reduce) in a CUDA graph when N > 1 (experimental)")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--render-frames", type=int, default=5)
     args = ap.parse_args()
@@ -265,7 +263,8 @@ def main():
 
     # ---- timed region 1b: the same step captured in ONE CUDA graph (Trainer.enable_cuda_graph) -- the product path
     graphed = False
-    if not args.no_graph and (world == 1 or args.graph_dist):
+    # N > 1 runs eagerly: capturing the step together with its NCCL all-reduce hung on 2 x B200 (round 1)
+    if not args.no_graph and world == 1:
         try:
             graphed = bool(trainer.enable_cuda_graph(resident[0]))
             for i in range(args.warmup):

@@ -108,6 +108,9 @@ class Trainer:
         random draws (stratified jitter, sigma noise) come from the graph-registered default CUDA generator.
         The NaN/Inf guard of the model runs in deferred mode (flag word inspected by `check_numerics()`)."""
         import os
+        if dist.is_initialized() and dist.get_world_size(self.allreduce.group) > 1:
+            # capturing the NCCL all-reduce together with the step hung on 2 x B200 (round 1, unresolved)
+            raise RuntimeError("Trainer.enable_cuda_graph supports world size 1 only")
         if self._graph is not None:
             return True
         dev = sample_batch["rays"].device

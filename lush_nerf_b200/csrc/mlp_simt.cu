@@ -9,6 +9,7 @@
 //   DGRAD C[m,k] = ( sum_n G[m,n] W[n,k] ) * (Mask[m,k] > 0)        (optionally accumulating)
 //   WGRAD C[n,k] += sum_m G[m,n] X[m,k]                              (split over m, fp32 atomics)
 // plus encode / encode-backward / bias-grad / relu-mask kernels.
+#include <stdlib.h>
 #include "mlp_common.cuh"
 
 namespace lush {
@@ -318,6 +319,24 @@ constexpr int64_t kInferChunkRows = 1 << 16;  // same row chunk as the reference
 
 using namespace lush;
 
+// fused small-network path (mlp_small.cu)
+bool lush_mlp_small_supported(const MlpLayout& L, int64_t M);
+int lush_mlp_small_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* params, const float* ray_batch,
+                       int ray_stride, const float* z, float* out, float* const* stash_ptrs, int64_t M, int S,
+                       cudaStream_t st);
+int lush_mlp_small_bwd(const MlpLayout& L, const float* params, const float* g_out, float* const* stash_ptrs,
+                       float* g_params, int64_t M, int S, cudaStream_t st);
+static void small_stash_ptrs(const SimtStash* s, float** p) {
+  for (int i = 0; i < 4 + kMaxDepth; ++i) p[i] = nullptr;
+  if (s == nullptr) return;
+  p[0] = s->enc_pts; p[1] = s->enc_views; p[2] = s->feat; p[3] = s->hv;
+  for (int i = 0; i < kMaxDepth; ++i) p[4 + i] = s->h[i];
+}
+static bool small_path_enabled() {
+  const char* e = getenv("LUSH_SMALL_MLP");   // LUSH_SMALL_MLP=0: always use the layer-by-layer GEMM path
+  return !(e && e[0] == '0');
+}
+
 size_t lush_mlp_simt_stash_bytes(const MlpLayout& L, int64_t R, int S) {
   return carve_stash(L, nullptr, R * S, R).floats * sizeof(float);
 }
@@ -373,6 +392,17 @@ int lush_mlp_simt_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float
                       void* workspace, size_t workspace_bytes, int64_t R, int S, cudaStream_t st) {
   const int64_t M = R * S;
   Launcher go{st};
+  if (small_path_enabled() && lush_mlp_small_supported(L, M)) {   // few rows of a narrow net: one fused launch
+    float* p[4 + kMaxDepth];
+    if (stash != nullptr) {
+      SimtStash s = carve_stash(L, (float*)stash, M, R);
+      for (int i = L.D; i < kMaxDepth; ++i) s.h[i] = nullptr;
+      small_stash_ptrs(&s, p);
+    } else {
+      small_stash_ptrs(nullptr, p);
+    }
+    return lush_mlp_small_fwd(L, desc, params, ray_batch, ray_stride, z, out, p, M, S, st);
+  }
   // encoded view directions, once per ray (the reference re-encodes them per sample, lushnerf.py:241-243)
   if (stash != nullptr) {
     SimtStash s = carve_stash(L, (float*)stash, M, R);
@@ -425,6 +455,12 @@ int lush_mlp_simt_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float
     return LUSH_EWORKSPACE;
   }
   SimtStash s = carve_stash(L, (float*)const_cast<void*>(stash), M, R);
+  if (g_ray_batch == nullptr && small_path_enabled() && lush_mlp_small_supported(L, M)) {
+    float* p[4 + kMaxDepth];
+    for (int i = L.D; i < kMaxDepth; ++i) s.h[i] = nullptr;
+    small_stash_ptrs(&s, p);
+    return lush_mlp_small_bwd(L, params, g_out, p, g_params, M, S, st);
+  }
   float* gA = (float*)workspace;                 // [M, W]   gradient wrt current activation
   float* gB = gA + (size_t)M * W;                // [M, W]
   float* g_enc = gB + (size_t)M * W;             // [M, in_ch]   (two contributions: layer 0, skip layer)

@@ -41,11 +41,18 @@ __device__ __forceinline__ void small_dense(int t, int N, const float* __restric
       const float* x = seg ? x1 : x0;
       const int ld = seg ? ld1 : ld0, K = seg ? K1 : K0, wc = seg ? wc1 : wc0;
       if (x == nullptr) continue;
+      // every thread streams its own weight row: 16-byte loads when the row segment is aligned (4x fewer L1 requests)
+      const bool vec = ((fan | wc) & 3) == 0 && (K & 3) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0;
 #pragma unroll 2
       for (int kq = 0; kq < K; kq += 4) {     // shared rows are zero-padded to a multiple of 4
         float w[4];
+        if (vec) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + wc + kq));
+          w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = (kq + j < K) ? __ldg(wrow + wc + kq + j) : 0.f;
+          for (int j = 0; j < 4; ++j) w[j] = (kq + j < K) ? __ldg(wrow + wc + kq + j) : 0.f;
+        }
 #pragma unroll
         for (int r = 0; r < TM; ++r) {
           const float4 a = *reinterpret_cast<const float4*>(x + r * ld + kq);

@@ -112,13 +112,58 @@ sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weig
   }
 }
 
+// ascending bitonic sort of 32*KPL keys held in shared memory by one warp: lane l owns keys [l*KPL, (l+1)*KPL)
+// in registers; stages with partner distance >= KPL exchange through shuffles, smaller ones stay in the lane
+template <int KPL>
+__device__ __forceinline__ void warp_bitonic_sort_regs(float* __restrict__ keys, int lane) {
+  float v[KPL];
+#pragma unroll
+  for (int q = 0; q < KPL; ++q) v[q] = keys[lane * KPL + q];
+#pragma unroll
+  for (int k = 2; k <= 32 * KPL; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= KPL) {
+        const int lj = j / KPL;                                // partner lane distance
+        const bool lower = (lane & lj) == 0;                   // this lane holds the lower index of each pair
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+          const int e = lane * KPL + q;
+          const bool up = (e & k) == 0;
+          const float o = __shfl_xor_sync(0xffffffffu, v[q], lj);
+          const float mn = fminf(v[q], o), mx = fmaxf(v[q], o);
+          v[q] = (lower == up) ? mn : mx;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+          if ((q & j) == 0) {
+            const int e = lane * KPL + q;
+            const bool up = (e & k) == 0;
+            const float a = v[q], b = v[q | j];
+            const float mn = fminf(a, b), mx = fmaxf(a, b);
+            v[q] = up ? mn : mx;
+            v[q | j] = up ? mx : mn;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < KPL; ++q) keys[lane * KPL + q] = v[q];
+  __syncwarp();
+}
+
 // Fused: z_mid, cdf from weights[1:-1], N samples, sort(cat(z, samples)), z_std.
-// smem per warp: cdf[S-1] + bins[S-1] + w[S-2] + sort[P], P = next pow2 >= S+N
+// The coarse z of a ray are already ascending (stratified bins), so only the N new samples are sorted (bitonic,
+// PN = next pow2 >= N keys) and the two ascending lists are MERGED by rank: z[i] lands at i + #{samples < z[i]},
+// sample k at k + #{z <= sample_k} (binary searches in shared memory) -- the same values torch.sort produces.
+// smem per warp: cdf[S-1] + bins[S-1] + w[S-1] + z[S] + samples[PN] + out[S+N]
 __global__ void __launch_bounds__(kSamplerWarps * 32)
 sample_merge_kernel(const float* __restrict__ z, const float* __restrict__ weights,
                     const float* __restrict__ u, int64_t u_stride, float* __restrict__ z_fine,
                     float* __restrict__ z_samples, float* __restrict__ z_std, int64_t R, int S, int N,
-                    int P, int per_warp) {
+                    int PN, int per_warp) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t r = (int64_t)blockIdx.x * kSamplerWarps + wid;
@@ -127,11 +172,13 @@ sample_merge_kernel(const float* __restrict__ z, const float* __restrict__ weigh
   float* s_cdf = smem + wid * per_warp;
   float* s_bins = s_cdf + nb;
   float* s_w = s_bins + nb;
-  float* s_sort = s_w + nb;  // (nb-1 used) keep simple alignment
-  for (int j = lane; j < S; j += 32) s_sort[j] = z[r * S + j];
+  float* s_z = s_w + nb;       // (nb-1 used) keep simple alignment
+  float* s_smp = s_z + S;
+  float* s_out = s_smp + PN;
+  for (int j = lane; j < S; j += 32) s_z[j] = z[r * S + j];
   for (int j = lane; j < S - 2; j += 32) s_w[j] = weights[r * S + j + 1];
   __syncwarp();
-  for (int j = lane; j < nb; j += 32) s_bins[j] = 0.5f * (s_sort[j + 1] + s_sort[j]);
+  for (int j = lane; j < nb; j += 32) s_bins[j] = 0.5f * (s_z[j + 1] + s_z[j]);
   warp_cdf_build(s_w, s_cdf, nb - 1, lane);
   __syncwarp();
   float sum = 0.f;
@@ -139,38 +186,58 @@ sample_merge_kernel(const float* __restrict__ z, const float* __restrict__ weigh
     float uu = u[r * u_stride + k];
     int inds;
     float s = invert_cdf(s_cdf, s_bins, nb, uu, inds);
-    s_sort[S + k] = s;
+    s_smp[k] = s;
     z_samples[r * N + k] = s;
     sum += s;
   }
-  for (int j = S + N + lane; j < P; j += 32) s_sort[j] = INFINITY;
+  for (int j = N + lane; j < PN; j += 32) s_smp[j] = INFINITY;
   if (z_std != nullptr) {  // population std (torch.std(unbiased=False))
     sum = warp_sum(sum);
     float mean = sum / (float)N, sq = 0.f;
     __syncwarp();
     for (int k = lane; k < N; k += 32) {
-      float d = s_sort[S + k] - mean;
+      float d = s_smp[k] - mean;
       sq += d * d;
     }
     sq = warp_sum(sq);
     if (lane == 0) z_std[r] = sqrtf(sq / (float)N);
   }
   __syncwarp();
-  // bitonic sort of P keys in shared memory (one warp)
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = lane; t < P / 2; t += 32) {
-        // t-th compare-exchange pair of this stage
-        int i = ((t / j) * 2 * j) + (t % j);
-        int l = i + j;
-        bool up = ((i & k) == 0);
-        float a = s_sort[i], b = s_sort[l];
-        if ((a > b) == up) { s_sort[i] = b; s_sort[l] = a; }
+  // bitonic sort of the PN sample keys by one warp: in registers (KPL consecutive keys per lane, shuffles for the
+  // cross-lane stages) when PN is 32..256, in shared memory otherwise
+  if (PN == 32) warp_bitonic_sort_regs<1>(s_smp, lane);
+  else if (PN == 64) warp_bitonic_sort_regs<2>(s_smp, lane);
+  else if (PN == 128) warp_bitonic_sort_regs<4>(s_smp, lane);
+  else if (PN == 256) warp_bitonic_sort_regs<8>(s_smp, lane);
+  else {
+    for (int k = 2; k <= PN; k <<= 1) {
+      for (int j = k >> 1, lj = 31 - __clz(k >> 1); j > 0; j >>= 1, --lj) {
+        for (int t = lane; t < PN / 2; t += 32) {
+          const int i = ((t >> lj) << (lj + 1)) | (t & (j - 1));   // t-th compare-exchange pair of this stage
+          const int l = i + j;
+          const bool up = ((i & k) == 0);
+          const float a = s_smp[i], b = s_smp[l];
+          if ((a > b) == up) { s_smp[i] = b; s_smp[l] = a; }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
-  for (int j = lane; j < S + N; j += 32) z_fine[r * (S + N) + j] = s_sort[j];
+  // merge by rank
+  for (int i = lane; i < S; i += 32) {
+    const float v = s_z[i];
+    int lo = 0, hi = N;                       // #{samples < v}
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_smp[mid] < v) lo = mid + 1; else hi = mid; }
+    s_out[i + lo] = v;
+  }
+  for (int k = lane; k < N; k += 32) {
+    const float v = s_smp[k];
+    int lo = 0, hi = S;                       // #{z <= v}
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_z[mid] <= v) lo = mid + 1; else hi = mid; }
+    s_out[k + lo] = v;
+  }
+  __syncwarp();
+  for (int j = lane; j < S + N; j += 32) z_fine[r * (S + N) + j] = s_out[j];
 }
 
 }  // namespace lush
@@ -206,9 +273,9 @@ extern "C" int lush_sample_merge(const float* z, const float* weights, const flo
   LUSH_REQUIRE(R >= 0 && S >= 3 && N >= 1, "sample_merge: need S >= 3 and N >= 1");
   LUSH_REQUIRE(S + N <= 2048, "sample_merge: S+N > 2048 is not supported");
   if (R == 0) return 0;
-  int P = 1;
-  while (P < S + N) P <<= 1;
-  int per_warp = 3 * (S - 1) + P;
+  int P = 1;                      // sort width of the N new samples
+  while (P < N) P <<= 1;
+  int per_warp = 3 * (S - 1) + S + P + (S + N);
   size_t smem = (size_t)kSamplerWarps * per_warp * sizeof(float);
   if (smem > 48 * 1024) {
     int rc = check_cuda(cudaFuncSetAttribute(sample_merge_kernel,

@@ -95,3 +95,17 @@ class SyntheticLLFF:
         sl = slice(s, s + N_rand)
         return dict(rays=self.rays[sl].permute(0, 2, 1), rgbsf=self.rgbsf[sl], fq_mask=self.fq_mask[sl],
                     images_idx=self.images_idx[sl])
+
+
+def scene_mlp_for_tools(device="cuda", seed=0, requires_grad=False):
+    """(flat, views, desc) of a randomly initialised 8x256 scene MLP (reference initialisers) for the profiling /
+    benchmarking tools under tools/: the flat fp32 arena, the parameter views in state_dict order, the MlpDesc."""
+    import torch
+    from .utils.run_lushnerf_helpers import NeRF
+    torch.manual_seed(seed)
+    net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True).to(device)
+    flat = net.flat_params()
+    views = list(net._ordered_params())
+    for v in views:
+        v.requires_grad_(requires_grad)
+    return flat, views, net._desc

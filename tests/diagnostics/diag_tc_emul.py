@@ -2,7 +2,7 @@
 same loss scale) and fp32 accumulation.  Agreement here at ~1e-3 isolates kernel correctness from the
 inherent ReLU-mask flips that separate any reduced-precision forward from the fp32 one."""
 import sys, os, math
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import torch.nn.functional as F
 from lush_nerf_b200 import _lib, ops

@@ -158,7 +158,7 @@ def test_tc_backward_vs_fp32_general(det_state, R, S, need_in):
     """General (ReLU) regime vs exact fp32.  A reduced-precision forward (fp16 or TF32 operands alike) moves
     pre-activations by ~3e-4, which flips the ReLU gate of the ~0.1% of units that sit that close to zero; each
     flip adds/removes one full gradient entry, so per-tensor relative L2 deviations of 2-4% are inherent
-    (tools/diag_tc_emul.py shows tensors without flips agree to 1e-4).  Stated tolerance: 8e-2 relative L2 and
+    (tests/diagnostics/diag_tc_emul.py shows tensors without flips agree to 1e-4).  Stated tolerance: 8e-2 relative L2 and
     cosine similarity >= 0.997 per parameter tensor; heads (no gate in between) 2e-3."""
     nets, _ = det_state
     desc = _lib.MlpDesc(8, 256, 10, 4, 4, 0)

@@ -88,13 +88,8 @@ def stress(R=65536):
 
 
 def mlp(R=32768, S=128):
-    from oracle import lush_oracle as O
-    nets = O.det_nets()
-    flat = torch.cat([nets["coarse"][n].reshape(-1) for n, _ in O.mlp_param_shapes(8, 256, 63, 27, 4)]).to(DEV)
-    views, off = [], 0
-    for _, shp in O.mlp_param_shapes(8, 256, 63, 27, 4):
-        n = int(np.prod(shp)); views.append(flat[off:off + n].view(shp)); off += n
-    desc = _lib.MlpDesc(8, 256, 10, 4, 4, 0)
+    from lush_nerf_b200.synthetic import scene_mlp_for_tools
+    flat, views, desc = scene_mlp_for_tools(DEV)
     rb = torch.zeros(R, 11, device=DEV)
     rb[:, :3] = torch.rand(R, 3, device=DEV) * 2 - 1
     rb[:, 3:6] = torch.randn(R, 3, device=DEV) * 0.3

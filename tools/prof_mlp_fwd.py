@@ -3,16 +3,11 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from lush_nerf_b200 import _lib, ops
-from oracle import lush_oracle as O
+from lush_nerf_b200.synthetic import scene_mlp_for_tools
 DEV = "cuda"
 mode = sys.argv[1] if len(sys.argv) > 1 else "fwd"
 R, S = 8192, 128
-nets = O.det_nets()
-flat = torch.cat([nets["coarse"][n].reshape(-1) for n, _ in O.mlp_param_shapes(8, 256, 63, 27, 4)]).to(DEV)
-views, off = [], 0
-for _, shp in O.mlp_param_shapes(8, 256, 63, 27, 4):
-    n = int(np.prod(shp)); views.append(flat[off:off + n].view(shp).requires_grad_(mode != "fwd")); off += n
-desc = _lib.MlpDesc(8, 256, 10, 4, 4, 0)
+flat, views, desc = scene_mlp_for_tools(DEV, requires_grad=(mode != "fwd"))
 rb = torch.zeros(R, 11, device=DEV)
 rb[:, :3] = torch.rand(R, 3, device=DEV) * 2 - 1
 rb[:, 3:6] = torch.randn(R, 3, device=DEV) * 0.3

@@ -5,15 +5,10 @@ os.environ["LUSH_CHAIN_DEBUG"] = os.environ.get("LUSH_CHAIN_DEBUG", "2")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from lush_nerf_b200 import _lib, ops
-from oracle import lush_oracle as O
+from lush_nerf_b200.synthetic import scene_mlp_for_tools
 DEV = "cuda"
 R, S = 8192, 128
-nets = O.det_nets()
-flat = torch.cat([nets["coarse"][n].reshape(-1) for n, _ in O.mlp_param_shapes(8, 256, 63, 27, 4)]).to(DEV)
-views, off = [], 0
-for _, shp in O.mlp_param_shapes(8, 256, 63, 27, 4):
-    n = int(np.prod(shp)); views.append(flat[off:off + n].view(shp)); off += n
-desc = _lib.MlpDesc(8, 256, 10, 4, 4, 0)
+flat, views, desc = scene_mlp_for_tools(DEV)
 rb = torch.zeros(R, 11, device=DEV); rb[:, :3] = torch.rand(R, 3, device=DEV); rb[:, 3:6] = torch.randn(R, 3, device=DEV) * 0.3
 rb[:, 8:11] = torch.nn.functional.normalize(torch.randn(R, 3, device=DEV), dim=-1)
 z = torch.rand(R, S, device=DEV).sort(-1)[0]

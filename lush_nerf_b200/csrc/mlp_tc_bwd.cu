@@ -24,6 +24,7 @@ enum BwdEpi { BE_VIEWS = 0, BE_FEAT = 1, BE_TRUNK = 2, BE_ENC = 3 };
 struct BwdPlan {
   int grec_bytes, grec_v, grec_f, grec_l0;
   int has_enc;          // d/d gamma(x) is produced (two [128 x 64] fp16 blobs per tile: skip layer, layer 0)
+  int has_skip_enc;     // ... and the skip-layer blob (slot 0) exists
 };
 
 struct BPackJob {
@@ -49,6 +50,7 @@ static void make_bwd_chain(const MlpLayout& L, bool need_in, ChainPlan& C, BwdPl
   B.grec_l0 = HV_BYTES + H_BYTES;
   B.grec_bytes = B.grec_l0 + L.D * H_BYTES;
   B.has_enc = need_in ? 1 : 0;
+  B.has_skip_enc = 0;
   int n = 0;
   int64_t off = 0;
   auto add = [&](int N, int pre16, int h_slices, int wait_a, int writes_a, int free_enc, int epi, int p0, int off0,
@@ -72,6 +74,7 @@ static void make_bwd_chain(const MlpLayout& L, bool need_in, ChainPlan& C, BwdPl
     if (is_skip && need_in) {
       add(64, 0, 8, prev_wrote, 0, 0, BE_ENC, 0, 0, L.pts_w[l], L.pts_in[l], 0, L.in_ch, 0, 0);
       prev_wrote = 0;
+      B.has_skip_enc = 1;
     }
     // the last dZ has a consumer inside the chain only when d/d gamma(x) is wanted
     add(TW, 0, 8, prev_wrote, (l > 1 || need_in) ? 1 : 0, 0, BE_TRUNK, l - 1, B.grec_l0 + (l - 1) * H_BYTES, L.pts_w[l],
@@ -270,7 +273,7 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
 __global__ void __launch_bounds__(128)
 enc_bwd_kernel(const uint8_t* __restrict__ genc, const float* __restrict__ ray_batch, int ray_stride,
                const float* __restrict__ z, const unsigned* __restrict__ scale_buf, float* __restrict__ g_x,
-               int64_t M, int S, int L_pts) {
+               int64_t M, int S, int L_pts, int has_skip) {
   const int64_t tile = blockIdx.x;
   const int row = threadIdx.x;
   const int64_t m = tile * TROWS + row;
@@ -280,7 +283,11 @@ enc_bwd_kernel(const uint8_t* __restrict__ genc, const float* __restrict__ ray_b
 #pragma unroll
   for (int gq = 0; gq < 8; ++gq) {
     float v0[8], v1[8];
-    unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 0) * (int64_t)ENC_BYTES + stash_off(8, row, gq)), v0);
+    if (has_skip) unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 0) * (int64_t)ENC_BYTES + stash_off(8, row, gq)), v0);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v0[i] = 0.f;
+    }
     unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 1) * (int64_t)ENC_BYTES + stash_off(8, row, gq)), v1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) ge[gq * 8 + i] = v0[i] + v1[i];
@@ -765,7 +772,8 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
     LUSH_LAUNCH_CHECK("head_grads");
   }
   if (need_in) {
-    enc_bwd_kernel<<<(unsigned)ntiles, 128, 0, st>>>(genc, ray_batch, ray_stride, z, scale_buf, gx, M, S, desc->L_pts);
+    enc_bwd_kernel<<<(unsigned)ntiles, 128, 0, st>>>(genc, ray_batch, ray_stride, z, scale_buf, gx, M, S, desc->L_pts,
+                                                     B.has_skip_enc);
     LUSH_LAUNCH_CHECK("enc_bwd");
     ray_grad_reduce_kernel<<<(unsigned)((R + 3) / 4), 128, 0, st>>>(gx, z, gstash, B.grec_bytes, B.grec_v, params,
                                                                    L.views_w, L.W + L.in_ch_v, L.in_ch_v,

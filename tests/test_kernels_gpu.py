@@ -361,3 +361,39 @@ def test_mlp_golden_outputs_through_public_mlpforward(golden, det_state):
     pts, views = golden["mlp/pts"].to(DEV), golden["mlp/views"].to(DEV)
     out = m.mlpforward(pts[:, None, :], views, m.mlp_coarse)
     close(out[:, 0, :], golden["mlp/coarse/out"], 5e-5, "NeRF.forward golden")
+
+
+@pytest.mark.parametrize("R,S", [(1024, 1), (77, 3)])
+def test_small_mlp_fused_backward_vs_oracle(det_state, R, S):
+    """Noise MLP with detached inputs (the model's call pattern): fused forward AND fused backward kernels
+    (csrc/mlp_small.cu) against the oracle, and against the layer-by-layer GEMM path (LUSH_SMALL_MLP=0)."""
+    import os
+    nets, _ = det_state
+    D, W, mode = 4, 128, 1
+    rb, z = mlp_case("noise", R, S, 9)
+    p = {k: t.clone().requires_grad_(True) for k, t in nets["noise"].items()}
+    ref = O.mlp_on_rays(p, rb, z, D, W, 10, 4, 4, mode)
+    cot = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (ref * cot).sum().backward()
+    desc = _lib.MlpDesc(D, W, 10, 4, 4, mode)
+    shapes = O.mlp_param_shapes(D, W, 63, 27, 4)
+    grads = {}
+    for small in ("1", "0"):
+        os.environ["LUSH_SMALL_MLP"] = small
+        flat = torch.cat([nets["noise"][n].reshape(-1) for n, _ in shapes]).to(DEV)
+        views, off = [], 0
+        for _, shp in shapes:
+            n = int(np.prod(shp)); views.append(flat[off:off + n].view(shp).requires_grad_(True)); off += n
+        out = ops.mlp_apply(rb.to(DEV), z.to(DEV), desc, 0, flat, views)
+        close(out, ref, 3e-5 * max(1.0, ref.abs().max().item()), "small mlp out")
+        (out * cot.to(DEV)).sum().backward()
+        grads[small] = [v.grad for v in views]
+    os.environ.pop("LUSH_SMALL_MLP", None)
+    for (name, _), g1, g0 in zip(shapes, grads["1"], grads["0"]):
+        gref = p[name].grad
+        if gref is None:
+            assert g1 is None or float(g1.abs().max()) == 0.0
+            continue
+        tol = 2e-5 * max(1.0, gref.abs().max().item()) * max(1.0, (R * S) ** 0.5 / 8)
+        close(g1, gref, tol, f"fused grad {name}")
+        close(g1, g0, tol, f"fused vs gemm path {name}")

@@ -239,3 +239,30 @@ def test_tc_many_tiles_per_cta_forward_and_backward():
         tol = 2e-3 if name.startswith(("alpha_linear", "rgb_linear")) else 8e-2
         assert _rel(g1, g0) <= tol, (name, _rel(g1, g0))
     assert _rel(res[1][2][:, 0:6], res[0][2][:, 0:6]) <= 8e-2
+
+
+@pytest.mark.parametrize("D,skip,need_in", [(4, -1, True), (6, 2, True), (6, 2, False), (2, -1, True)])
+def test_tc_backward_other_topologies(D, skip, need_in):
+    """The dgrad chain and the wgrad job list are built from (D, skip) at run time; compare with the fp32 path."""
+    shapes = O.mlp_param_shapes(D, 256, 63, 27, skip)
+    p = O.det_mlp_params(D, 256, 63, 27, skip, 70 + D)
+    desc = _lib.MlpDesc(D, 256, 10, 4, skip if skip >= 0 else 99, 0)
+    rb, z = mlp_case("coarse", 300, 48, D)
+    gout = torch.randn(300, 48, 4, generator=torch.Generator().manual_seed(D)).to(DEV)
+    res = []
+    for impl in (0, 1):
+        flat = torch.cat([p[n].reshape(-1) for n, _ in shapes]).to(DEV)
+        views, off = [], 0
+        for _, shp in shapes:
+            n = int(np.prod(shp)); views.append(flat[off:off + n].view(shp).requires_grad_(True)); off += n
+        rbg = rb.to(DEV).requires_grad_(need_in)
+        out = ops.mlp_apply(rbg, z.to(DEV), desc, impl, flat, views)
+        out.backward(gout)
+        res.append((out.detach(), [v.grad for v in views], rbg.grad if need_in else None))
+    scale = res[0][0].abs().amax().item()
+    assert (res[1][0] - res[0][0]).abs().max().item() / scale <= 4e-3
+    for (name, _), g1, g0 in zip(shapes, res[1][1], res[0][1]):
+        tol = 2e-3 if name.startswith(("alpha_linear", "rgb_linear")) else 8e-2
+        assert _rel(g1, g0) <= tol, (D, skip, name, _rel(g1, g0))
+    if need_in:
+        assert _rel(res[1][2][:, 0:6], res[0][2][:, 0:6]) <= 8e-2

@@ -297,32 +297,36 @@ def main():
     # ---- render leg (BASELINE configs[3]): --render_only style full frames, chunk 32768, 64+64, det sampling
     render = None
     if world == 1 and not args.no_render:
-        from lush_nerf_b200.synthetic import spiral_poses
-        poses = torch.from_numpy(spiral_poses(args.render_frames + 2, radius_scale=2.0)).to(dev)
-        rk = dict(perturb=False, N_importance=N_IMPORTANCE, N_samples=N_SAMPLES, use_viewdirs=True, white_bkgd=False,
-                  raw_noise_std=0.0, inference=True, near=0.0, far=1.0)
-        model.eval()
-        with torch.no_grad():
-            model(H, W, trainer.K, chunk=1024 * 32, poses=poses[:2], render_kwargs=dict(rk))   # warm-up frames
-            torch.cuda.synchronize()
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            rsampler = ClockSampler(local)
-            rsampler.start()
-            mlp_events.clear()
-            ops.MLP_EVENT_SINK = mlp_events
-            r0.record()
-            rgbs, _, _ = model(H, W, trainer.K, chunk=1024 * 32, poses=poses[2:], render_kwargs=dict(rk))
-            r1.record()
-            torch.cuda.synchronize()
-            ops.MLP_EVENT_SINK = None
-        rclocks = rsampler.stop()
-        ms_frame = r0.elapsed_time(r1) / args.render_frames
-        mlp_ms_frame = sum(a.elapsed_time(b) for lab, a, b in mlp_events if lab == "fwd") / args.render_frames
-        fl = FLOP_FWD_PER_SAMPLE * H * W * SAMPLES_PER_RAY
-        render = {"ms_per_frame": ms_frame, "frames": args.render_frames, "rays_per_s": H * W / (ms_frame * 1e-3),
-                  "image": f"{H}x{W}", "chunk": 32768, "mlp_ms_per_frame": mlp_ms_frame,
-                  "mlp_tflops": fl / (mlp_ms_frame * 1e-3) / 1e12 if mlp_ms_frame > 0 else None,
-                  "finite": bool(torch.isfinite(rgbs).all().item()), "clocks": rclocks}
+      try:   # a failure of this secondary leg must not cost the headline line
+          from lush_nerf_b200.synthetic import spiral_poses
+          poses = torch.from_numpy(spiral_poses(args.render_frames + 2, radius_scale=2.0)).to(dev)
+          rk = dict(perturb=False, N_importance=N_IMPORTANCE, N_samples=N_SAMPLES, use_viewdirs=True, white_bkgd=False,
+                    raw_noise_std=0.0, inference=True, near=0.0, far=1.0)
+          model.eval()
+          with torch.no_grad():
+              model(H, W, trainer.K, chunk=1024 * 32, poses=poses[:2], render_kwargs=dict(rk))   # warm-up frames
+              torch.cuda.synchronize()
+              r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+              rsampler = ClockSampler(local)
+              rsampler.start()
+              mlp_events.clear()
+              ops.MLP_EVENT_SINK = mlp_events
+              r0.record()
+              rgbs, _, _ = model(H, W, trainer.K, chunk=1024 * 32, poses=poses[2:], render_kwargs=dict(rk))
+              r1.record()
+              torch.cuda.synchronize()
+              ops.MLP_EVENT_SINK = None
+          rclocks = rsampler.stop()
+          ms_frame = r0.elapsed_time(r1) / args.render_frames
+          mlp_ms_frame = sum(a.elapsed_time(b) for lab, a, b in mlp_events if lab == "fwd") / args.render_frames
+          fl = FLOP_FWD_PER_SAMPLE * H * W * SAMPLES_PER_RAY
+          render = {"ms_per_frame": ms_frame, "frames": args.render_frames, "rays_per_s": H * W / (ms_frame * 1e-3),
+                    "image": f"{H}x{W}", "chunk": 32768, "mlp_ms_per_frame": mlp_ms_frame,
+                    "mlp_tflops": fl / (mlp_ms_frame * 1e-3) / 1e12 if mlp_ms_frame > 0 else None,
+                    "finite": bool(torch.isfinite(rgbs).all().item()), "clocks": rclocks}
+          model.train()
+      except Exception as e:
+        render = {"error": f"{type(e).__name__}: {e}"}
         model.train()
 
     if rank == 0:
@@ -369,11 +373,13 @@ def main():
             "final_loss": loss_host,
             "render": render,
         }
+        line["cpu_baseline"] = None
         if not args.no_cpu_baseline and world == 1:
-            val, ms, cores, sample = cpu_reference_run(steps=2, warmup=1)
-            line["cpu_baseline"] = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
-        else:
-            line["cpu_baseline"] = None
+            try:
+                val, ms, cores, sample = cpu_reference_run(steps=2, warmup=1)
+                line["cpu_baseline"] = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+            except Exception as e:
+                line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -175,6 +175,40 @@ int lush_blend_tonemap_bwd(const float* rgb, const float* ccw, const float* nois
                            int gamma, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training loss of the blurred colours, value and gradient in one launch.
+ * Replaces reference run_lushnerf.py:652-661 (img2mse / img2mae of rgb_blur and rgb0_blur against the
+ * target pixels, weighted 0.5 each) together with the autograd nodes those lines create.
+ *   loss[0]   = 0.5*mean(d^2) + 0.5*mean|d| + 0.5*mean(d0^2) + 0.5*mean|d0|,  d = blur - target, d0 = blur0 - target
+ *   g_blur[i] = (d_i + 0.5*sign(d_i)) / n      (same for g_blur0);  blur0 / g_blur0 may be null (single term pair)
+ * n = number of floats (3 * pixels).  n <= 32768 runs as one CTA: bit-reproducible sum order.
+ * ------------------------------------------------------------------------------------------- */
+int lush_blur_loss(const float* blur, const float* blur0, const float* target, int64_t n, float* loss,
+                   float* g_blur, float* g_blur0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-tensor Adam step.  Replaces the reference's optimizer = torch.optim.Adam(params=grad_vars, lr=lrate,
+ * betas=(0.9, 0.999)) and its optimizer.step() (run_lushnerf.py:359-371, :675-677): no weight decay, no amsgrad.
+ *   exp_avg += (1-beta1)*(grad-exp_avg);  exp_avg_sq = beta2*exp_avg_sq + (1-beta2)*grad^2
+ *   param  -= lr/(1-beta1^t) * exp_avg / (sqrt(exp_avg_sq)/sqrt(1-beta2^t) + eps),  t = steps[step_index] + 1
+ * `segs` is a HOST array (one entry per parameter tensor that has a gradient); lr[] (one learning rate per
+ * parameter group), steps[] (updates received so far, per tensor) and done_counter (one zero-initialised
+ * word) live on the DEVICE, so a captured CUDA graph follows learning-rate changes and keeps counting.
+ * The kernel increments steps[step_index] of every segment once.  Segments must not overlap.
+ * ------------------------------------------------------------------------------------------- */
+#define LUSH_ADAM_MAX_SEGS 64   /* tensors per launch; longer lists are split into several launches */
+typedef struct lush_adam_seg {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  int32_t step_index;
+  int32_t lr_index;
+} lush_adam_seg;
+int lush_adam_step(const lush_adam_seg* segs, int nseg, const float* lr, float* steps,
+                   unsigned int* done_counter, double beta1, double beta2, double eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Diagnostics (not on the product path): one-CTA tcgen05 GEMM D[128,N] = A[128,K] . B[N,K]^T over fp16
  * "tile-canonical" operand blobs, used by the GPU tests to pin the UMMA descriptor conventions that the
  * fused MLP kernels rely on.  a_mode / b_mode: 0 = K-major view, 1 = MN-major view of the blob.

@@ -19,6 +19,12 @@ class MlpDesc(Structure):
                 ("skip", c_int32), ("out_mode", c_int32)]
 
 
+class AdamSeg(Structure):
+    """Mirror of `struct lush_adam_seg`."""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("numel", c_int64), ("step_index", c_int32), ("lr_index", c_int32)]
+
+
 _P = c_void_p
 _SIGNATURES = {
     "lush_abi_version": (c_int, []),
@@ -45,6 +51,8 @@ _SIGNATURES = {
     "lush_rbk_warp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "lush_blend_tonemap_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "lush_blend_tonemap_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "lush_blur_loss": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P]),
+    "lush_adam_step": (c_int, [POINTER(AdamSeg), c_int, _P, _P, _P, c_double, c_double, c_double, _P]),
     "lush_tc_selftest": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "lush_tc_microbench": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P]),
     "lush_debug_read_chain_trace": (c_int, [_P, c_int]),

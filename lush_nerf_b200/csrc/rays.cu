@@ -391,6 +391,57 @@ extern "C" int lush_rbk_warp_bwd(const float* rays, const float* r, const float*
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Training loss 0.5*MSE + 0.5*L1 on the fine and the coarse blurred colours, value AND gradient in one
+// launch (reference run_lushnerf.py:652-661: img2mse + img2mae on rgb_blur and rgb0_blur, 0.5 each).
+// One CTA when the batch is small, so the sum order (and the loss bits) are fixed from run to run.
+// ------------------------------------------------------------------------------------------------
+__global__ void blur_loss_kernel(const float* __restrict__ blur, const float* __restrict__ blur0,
+                                 const float* __restrict__ target, int64_t n, float inv_n,
+                                 float* __restrict__ loss, float* __restrict__ g_blur,
+                                 float* __restrict__ g_blur0) {
+  __shared__ float s_part[32];
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float t = target[i];
+    float d = blur[i] - t;
+    acc += 0.5f * (d * d + fabsf(d));
+    g_blur[i] = (d + 0.5f * (float)((d > 0.f) - (d < 0.f))) * inv_n;
+    if (blur0) {
+      float d0 = blur0[i] - t;
+      acc += 0.5f * (d0 * d0 + fabsf(d0));
+      g_blur0[i] = (d0 + 0.5f * (float)((d0 > 0.f) - (d0 < 0.f))) * inv_n;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) {
+      if (gridDim.x == 1) loss[0] = v * inv_n;
+      else atomicAdd(loss, v * inv_n);
+    }
+  }
+}
+
+extern "C" int lush_blur_loss(const float* blur, const float* blur0, const float* target, int64_t n,
+                              float* loss, float* g_blur, float* g_blur0, void* stream) {
+  LUSH_REQUIRE(blur && target && loss && g_blur && n > 0, "blur_loss: bad arguments");
+  LUSH_REQUIRE(!blur0 || g_blur0, "blur_loss: g_blur0 required with blur0");
+  int th = 1024;
+  unsigned blocks = n <= 32768 ? 1u : (unsigned)(ceil_div(n, (int64_t)th * 4) < 148 ? ceil_div(n, (int64_t)th * 4) : 148);
+  if (blocks > 1) {
+    cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream);
+    LUSH_REQUIRE(e == cudaSuccess, "blur_loss: memset failed: %s", cudaGetErrorString(e));
+  }
+  blur_loss_kernel<<<blocks, th, 0, (cudaStream_t)stream>>>(blur, blur0, target, n, 1.0f / (float)n, loss, g_blur,
+                                                            g_blur0);
+  LUSH_LAUNCH_CHECK("blur_loss");
+  return 0;
+}
+
 extern "C" int lush_blend_tonemap_fwd(const float* rgb, const float* ccw, const float* noise_raw,
                                       float* out_blur, float* out_pure, float* noise_rgb, int64_t N,
                                       int K, int gamma, void* stream) {

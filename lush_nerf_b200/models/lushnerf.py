@@ -93,8 +93,9 @@ class Rigid_Blurring_Kernel(nn.Module):
         extras = {k: (blend(v) if torch.is_tensor(v) and 1 <= v.dim() <= 3 else v) for k, v in extras.items()}
         return rgb, depth, acc, extras
 
-    def motion_params(self, rays_info):
-        h = e = self.view_embedding_layer(rays_info['images_idx'].squeeze(-1))
+    def _motion_mlp(self, e):
+        """e [rows, input_ch] -> (r, v, ccw) rows (reference :118-153)."""
+        h = e
         for i, l in enumerate(self.view_embed_linears):
             h = F.relu(l(h))
             if i in self.skips:
@@ -110,6 +111,19 @@ class Rigid_Blurring_Kernel(nn.Module):
         v = self.v_linear(hv) * self.rv_window
         w = torch.sigmoid(self.w_linear(hw))
         return r, v, w / (torch.sum(w, dim=-1, keepdims=True) + 1e-10)
+
+    def motion_params(self, rays_info):
+        """The motion parameters are a function of the image index alone, so when the table has fewer rows than
+        the batch the MLP runs once per IMAGE (num_img rows instead of N_rand) and the rays gather their image's
+        row; row-wise identical to the reference's per-ray evaluation (:118-153), 50x less work at 20 views."""
+        idx = rays_info['images_idx'].squeeze(-1)
+        table = getattr(self.view_embedding_layer, 'view_embed_layer', None)
+        if isinstance(table, nn.Embedding) and table.num_embeddings <= idx.numel() and table.max_norm is None:
+            r, v, w = self._motion_mlp(table.weight)
+            nr, nv = r.shape[-1], v.shape[-1]
+            per_ray = torch.cat([r, v, w], -1).index_select(0, idx.reshape(-1))
+            return per_ray[:, :nr], per_ray[:, nr:nr + nv], per_ray[:, nr + nv:]
+        return self._motion_mlp(self.view_embedding_layer(idx))
 
     def forward(self, rays, rays_info):
         r, v, w = self.motion_params(rays_info)

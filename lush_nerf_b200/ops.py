@@ -331,3 +331,33 @@ def blend_tonemap(rgb, ccw=None, noise_raw=None, K: int = 1, gamma: bool = True)
     if not rgb.is_cuda:
         raise RuntimeError("lush_nerf_b200.blend_tonemap needs CUDA tensors; there is no CPU fallback")
     return _BlendTonemap.apply(rgb.reshape(-1, 3), ccw, noise_raw, int(K), gamma)
+
+
+# ------------------------------------------------------------------------------------------------
+# Training loss (reference run_lushnerf.py:652-661), value + gradient in one launch
+# ------------------------------------------------------------------------------------------------
+class _BlurLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, blur, blur0, target):
+        blur, blur0, target = _f32c(blur), _f32c(blur0), _f32c(target)
+        loss = _empty((), blur)
+        g, g0 = torch.empty_like(blur), torch.empty_like(blur0)
+        check(lib().lush_blur_loss(ptr(blur, "rgb_blur"), ptr(blur0, "rgb0_blur"), ptr(target, "target"),
+                                   blur.numel(), ptr(loss), ptr(g), ptr(g0), stream()), "lush_blur_loss")
+        ctx.save_for_backward(g, g0)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        g, g0 = ctx.saved_tensors
+        return g * g_loss, g0 * g_loss, None
+
+
+def blur_loss(rgb_blur, rgb0_blur, target):
+    """0.5*MSE + 0.5*L1 of the fine and the coarse blurred colours against the target pixels."""
+    if not rgb_blur.is_cuda:
+        raise RuntimeError("lush_nerf_b200.blur_loss needs CUDA tensors; there is no CPU fallback")
+    if rgb_blur.shape != target.shape or rgb0_blur.shape != target.shape:
+        raise ValueError(f"blur_loss: shapes differ: {tuple(rgb_blur.shape)}, {tuple(rgb0_blur.shape)}, "
+                         f"{tuple(target.shape)}")
+    return _BlurLoss.apply(rgb_blur, rgb0_blur, target)

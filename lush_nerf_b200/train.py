@@ -11,9 +11,12 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from . import ops
+
 
 def lush_loss(rgb_blur, rgb0_blur, target):
-    """0.5*MSE + 0.5*L1 on the fine and coarse outputs (reference run_lushnerf.py:652-661, stage 1/2)."""
+    """0.5*MSE + 0.5*L1 on the fine and coarse outputs (reference run_lushnerf.py:652-661, stage 1/2), written
+    with torch ops: the definition the fused kernel `ops.blur_loss` (what Trainer runs) is tested against."""
     d, d0 = rgb_blur - target, rgb0_blur - target
     return 0.5 * (d * d).mean() + 0.5 * d.abs().mean() + 0.5 * (d0 * d0).mean() + 0.5 * d0.abs().mean()
 
@@ -67,12 +70,13 @@ class Trainer:
         noise = list(model.mlp_noise_coarse.parameters())
         noise_ids = {id(p) for p in noise}
         base = [p for p in params if id(p) not in noise_ids]
-        kw = dict(lr=lrate)
-        if fused_adam and params[0].is_cuda:
-            kw["fused"] = True
-            kw["capturable"] = True          # step counters live on the device: the step can be graph-captured
         # two parameter groups like the reference (run_lushnerf.py:359-371)
-        self.optimizer = torch.optim.Adam([{"params": base}, {"params": noise, "lr": lrate}], **kw)
+        groups = [{"params": base}, {"params": noise, "lr": lrate}]
+        if fused_adam and params[0].is_cuda:
+            from .optim import Adam          # one launch for all tensors; lr and step counters on the device
+            self.optimizer = Adam(groups, lr=lrate)
+        else:
+            self.optimizer = torch.optim.Adam(groups, lr=lrate)
         self.allreduce = FlatGradAllReduce(params, group)
         self.render_kwargs = render_kwargs or {}
         self.lrate, self.global_step = lrate, 0
@@ -83,7 +87,7 @@ class Trainer:
         out = m(self.H, self.W, self.K, chunk=chunk, rays=batch["rays"],
                 rays_info={"images_idx": batch["images_idx"]}, retraw=True, force_naive=force_naive,
                 allkernel=allkernel, kernel_pixel=batch["fq_mask"], **self.render_kwargs)
-        loss = lush_loss(out[0], out[1], batch["rgbsf"])
+        loss = ops.blur_loss(out[0], out[1], batch["rgbsf"])      # value + gradient, one launch
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
         self.allreduce()
@@ -93,6 +97,7 @@ class Trainer:
     def step(self, batch, force_naive=False, allkernel=True, chunk=1024 * 32):
         self.model.train()
         if self._graph is not None and not force_naive and allkernel:
+            self.optimizer._sync_lr()               # learning-rate edits reach the replay through device memory
             for k, v in self._static.items():       # H2D (or D2D) into the captured input buffers
                 v.copy_(batch[k], non_blocking=True)
             self._graph.replay()
@@ -113,6 +118,8 @@ class Trainer:
             raise RuntimeError("Trainer.enable_cuda_graph supports world size 1 only")
         if self._graph is not None:
             return True
+        if not hasattr(self.optimizer, "_sync_lr"):
+            raise RuntimeError("Trainer.enable_cuda_graph needs the device-side optimizer (fused_adam=True)")
         dev = sample_batch["rays"].device
         os.environ["LUSH_NUMERIC_GUARD"] = "off"    # no event queries / host copies inside the captured region
         self._static = {k: v.to(dev).clone() for k, v in sample_batch.items()}

@@ -407,6 +407,15 @@ def blend_tonemap(rgb, ccw, noise_raw, K: int, kind="gamma"):
     return blur, tonemap(blended, kind), nz
 
 
+def blur_loss(rgb_blur, rgb0_blur, target):
+    """Stage-1/2 training loss (run_lushnerf.py:652-661 with utils/run_lushnerf_helpers.py:9-10):
+    0.5*img2mse + 0.5*img2l1 of the fine and of the coarse blurred colours."""
+    mse = lambda x, y: torch.mean((x - y) ** 2)
+    l1 = lambda x, y: torch.mean(torch.abs(x - y))
+    return (0.5 * mse(rgb_blur, target) + 0.5 * l1(rgb_blur, target)
+            + 0.5 * mse(rgb0_blur, target) + 0.5 * l1(rgb0_blur, target))
+
+
 # ----------------------------------------------------------------------------------------------
 # a-12 NeRFAll.forward, training branches  (models/lushnerf.py:619-662)
 # ----------------------------------------------------------------------------------------------

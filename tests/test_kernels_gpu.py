@@ -302,6 +302,29 @@ def test_blend_tonemap_fwd_bwd():
     close(out[1], rgb ** (1 / 2.2), 2e-6, "tm")
 
 
+@pytest.mark.parametrize("N", [1, 33, 1024, 40000])
+def test_blur_loss_value_and_gradient(N):
+    """Fused loss kernel (one CTA for N*3 <= 32768, atomics above) vs the oracle's img2mse/img2l1 sum."""
+    g = torch.Generator().manual_seed(N)
+    tgt = torch.rand(N, 3, generator=g)
+    blur = (tgt + 0.2 * torch.randn(N, 3, generator=g)).requires_grad_(True)
+    blur0 = (tgt + 0.3 * torch.randn(N, 3, generator=g)).requires_grad_(True)
+    blur.data[0] = tgt[0]                      # exact zeros of the residual: sign(0) = 0 like torch.abs' backward
+    ref = O.blur_loss(blur, blur0, tgt)
+    (ref * 1.7).backward()
+    bc, b0c = (t.detach().to(DEV).requires_grad_(True) for t in (blur, blur0))
+    out = ops.blur_loss(bc, b0c, tgt.to(DEV))
+    assert out.dim() == 0
+    assert abs(out.item() - ref.item()) <= 2e-6 * max(1.0, abs(ref.item()))
+    (out * 1.7).backward()
+    assert rel_l2(bc.grad, blur.grad) < 1e-6 and rel_l2(b0c.grad, blur0.grad) < 1e-6
+    assert bc.grad[0].abs().max().item() == 0.0
+    if N * 3 <= 32768:                          # single-CTA path is bit-reproducible
+        assert ops.blur_loss(bc, b0c, tgt.to(DEV)).item() == out.item()
+    with pytest.raises(ValueError):
+        ops.blur_loss(bc, b0c[:-1] if N > 1 else b0c[:0], tgt.to(DEV))
+
+
 # ------------------------------------------------------------------------------------------------ MLP (fp32 SIMT)
 def mlp_case(net_name, R, S, seed):
     g = torch.Generator().manual_seed(seed)

@@ -175,6 +175,42 @@ int lush_blend_tonemap_bwd(const float* rgb, const float* ccw, const float* nois
                            int gamma, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Motion-parameter network of the rigid blurring kernel.
+ * Replaces Rigid_Blurring_Kernel.forward up to the warp call (reference models/lushnerf.py:118-147) and the
+ * autograd graph of those lines: view embedding -> trunk of ReLU layers (optional skip concat [e, h]) ->
+ * r / v / w branches -> r = lin*rv_window, v = lin*rv_window, w = sigmoid(lin), ccw = w / (sum(w) + 1e-10).
+ * The result depends on images_idx alone, so the network is evaluated once per row of the embedding table and
+ * every ray receives the row of its image.
+ *
+ * Activation row (row_width floats per image): columns [0, embed_dim) hold the embedding, every layer writes
+ * its out_dim outputs at out_off and reads in0 (and optionally in1, the concat partner) at columns that precede
+ * out_off.  Weights are torch nn.Linear tensors: w [out_dim, in0_dim + in1_dim] row-major, b [out_dim].
+ * r_off / v_off / w_off are the out_off of the three head layers (act = 0, widths 3M, 3M, M+1).
+ *   fwd: rows [n_img, row_width] receives the activation rows (needed by bwd); r, v [N, 3M]; ccw [N, M+1].
+ *   bwd: g_r / g_v / g_ccw may be null (no gradient); gw / gb of every layer are ACCUMULATED into (zero them
+ *        first); g_embed [n_img, embed_dim] is written (may be null).  images_idx values must lie in [0, n_img).
+ * ------------------------------------------------------------------------------------------- */
+#define LUSH_MOTION_MAX_LAYERS 24
+typedef struct lush_dense_layer {
+  const float* w;
+  const float* b;
+  float* gw;
+  float* gb;
+  int32_t in0_off, in0_dim, in1_off, in1_dim, out_off, out_dim, act; /* act: 0 = identity, 1 = ReLU */
+} lush_dense_layer;
+typedef struct lush_motion_net {
+  int32_t n_layers, row_width, embed_dim, num_motion;
+  int32_t r_off, v_off, w_off;
+  float rv_window;
+  lush_dense_layer layers[LUSH_MOTION_MAX_LAYERS];
+} lush_motion_net;
+int lush_rbk_motion_fwd(const lush_motion_net* net, const float* embed, int n_img, const int64_t* images_idx,
+                        int64_t N, float* rows, float* r, float* v, float* ccw, void* stream);
+int lush_rbk_motion_bwd(const lush_motion_net* net, int n_img, const int64_t* images_idx, int64_t N,
+                        const float* rows, const float* g_r, const float* g_v, const float* g_ccw,
+                        float* g_embed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Training loss of the blurred colours, value and gradient in one launch.
  * Replaces reference run_lushnerf.py:652-661 (img2mse / img2mae of rgb_blur and rgb0_blur against the
  * target pixels, weighted 0.5 each) together with the autograd nodes those lines create.

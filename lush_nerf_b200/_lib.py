@@ -25,6 +25,23 @@ class AdamSeg(Structure):
                 ("numel", c_int64), ("step_index", c_int32), ("lr_index", c_int32)]
 
 
+class DenseLayer(Structure):
+    """Mirror of `struct lush_dense_layer`."""
+    _fields_ = [("w", c_void_p), ("b", c_void_p), ("gw", c_void_p), ("gb", c_void_p),
+                ("in0_off", c_int32), ("in0_dim", c_int32), ("in1_off", c_int32), ("in1_dim", c_int32),
+                ("out_off", c_int32), ("out_dim", c_int32), ("act", c_int32)]
+
+
+MOTION_MAX_LAYERS = 24
+
+
+class MotionNet(Structure):
+    """Mirror of `struct lush_motion_net`."""
+    _fields_ = [("n_layers", c_int32), ("row_width", c_int32), ("embed_dim", c_int32), ("num_motion", c_int32),
+                ("r_off", c_int32), ("v_off", c_int32), ("w_off", c_int32), ("rv_window", c_float),
+                ("layers", DenseLayer * MOTION_MAX_LAYERS)]
+
+
 _P = c_void_p
 _SIGNATURES = {
     "lush_abi_version": (c_int, []),
@@ -51,6 +68,8 @@ _SIGNATURES = {
     "lush_rbk_warp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "lush_blend_tonemap_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "lush_blend_tonemap_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "lush_rbk_motion_fwd": (c_int, [POINTER(MotionNet), _P, c_int, _P, c_int64, _P, _P, _P, _P, _P]),
+    "lush_rbk_motion_bwd": (c_int, [POINTER(MotionNet), c_int, _P, c_int64, _P, _P, _P, _P, _P, _P]),
     "lush_blur_loss": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P]),
     "lush_adam_step": (c_int, [POINTER(AdamSeg), c_int, _P, _P, _P, c_double, c_double, c_double, _P]),
     "lush_tc_selftest": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -1,0 +1,297 @@
+// Motion-parameter network of the rigid blurring kernel, forward and backward in ONE launch each.
+// Replaces Rigid_Blurring_Kernel.forward up to the warp (reference models/lushnerf.py:118-147): view embedding ->
+// trunk (ReLU, optional skip concat) -> r / v / w branches -> r*window, v*window, w = sigmoid, w / (sum w + 1e-10).
+//
+// Everything up to (r, v, ccw) depends on the image index alone, so the network runs once per IMAGE (rows of
+// the embedding table) and every ray gathers the row of its image; the backward sums the per-ray gradients per
+// image first.  A CTA owns MOTION_ROWS images and keeps every activation of those rows in shared memory through
+// the whole network; a warp owns an output unit, its lanes stride the (contiguous) fan-in of that unit, so the
+// weights are read coalesced straight from L2 and never staged.  ~25 k parameters: the kernels are latency
+// bound by design -- they replace ~90 library launches of a few microseconds each.
+#include "common.cuh"
+
+namespace lush {
+
+constexpr int MOTION_ROWS = 8;
+constexpr int MOTION_THREADS = 512;
+
+__device__ __forceinline__ int motion_src(const lush_dense_layer& L, int k) {
+  return k < L.in0_dim ? L.in0_off + k : L.in1_off + (k - L.in0_dim);
+}
+
+// Pull every weight matrix (~100 KB in all) towards L1 at kernel start: the layer loop then waits on L1 hits
+// instead of one L2 round trip per output unit.
+__device__ __forceinline__ void motion_prefetch_weights(const lush_motion_net& net, int tid) {
+  for (int l = 0; l < net.n_layers; ++l) {
+    const lush_dense_layer& L = net.layers[l];
+    const int total = L.out_dim * (L.in0_dim + L.in1_dim);
+    for (int i = tid * 32; i < total; i += MOTION_THREADS * 32)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(L.w + i));
+  }
+}
+
+__global__ void __launch_bounds__(MOTION_THREADS)
+motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __restrict__ embed, int n_img,
+                  const int64_t* __restrict__ idx, int64_t N, float* __restrict__ rows,
+                  float* __restrict__ out_r, float* __restrict__ out_v, float* __restrict__ out_ccw) {
+  extern __shared__ float s_act[];                      // [MOTION_ROWS][rw]
+  const int rw = net.row_width, C = net.embed_dim, M = net.num_motion;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MOTION_THREADS / 32;
+  const int row0 = blockIdx.x * MOTION_ROWS;
+  const int nrows = min(MOTION_ROWS, n_img - row0);
+  motion_prefetch_weights(net, tid);
+  for (int t = tid; t < MOTION_ROWS * C; t += MOTION_THREADS) {
+    int r = t / C, k = t - r * C;
+    s_act[r * rw + k] = r < nrows ? embed[(int64_t)(row0 + r) * C + k] : 0.f;
+  }
+  __syncthreads();
+  for (int l = 0; l < net.n_layers; ++l) {
+    const lush_dense_layer& L = net.layers[l];
+    const int in_dim = L.in0_dim + L.in1_dim;
+    for (int o = warp; o < L.out_dim; o += nwarps) {
+      float acc[MOTION_ROWS];
+#pragma unroll
+      for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = 0.f;
+      const float* wrow = L.w + (int64_t)o * in_dim;
+      for (int k = lane; k < in_dim; k += 32) {
+        float w = wrow[k];
+        const float* a = s_act + motion_src(L, k);
+#pragma unroll
+        for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = fmaf(w, a[r * rw], acc[r]);
+      }
+      float mine = 0.f;
+#pragma unroll
+      for (int r = 0; r < MOTION_ROWS; ++r) {
+        float s = warp_sum(acc[r]);
+        if (lane == r) mine = s;
+      }
+      if (lane < MOTION_ROWS) {
+        mine += L.b[o];
+        s_act[lane * rw + L.out_off + o] = L.act ? fmaxf(mine, 0.f) : mine;
+      }
+    }
+    __syncthreads();
+  }
+  // stash the rows (pre-head values) for the backward
+  for (int t = tid; t < nrows * rw; t += MOTION_THREADS) rows[(int64_t)row0 * rw + t] = s_act[t];
+  __syncthreads();
+  // heads: r, v scaled by the window; w -> sigmoid -> normalised composition weights
+  for (int t = tid; t < MOTION_ROWS * 6 * M; t += MOTION_THREADS) {
+    int r = t / (6 * M), j = t - r * 6 * M;
+    int off = j < 3 * M ? net.r_off + j : net.v_off + (j - 3 * M);
+    s_act[r * rw + off] *= net.rv_window;
+  }
+  if (tid < MOTION_ROWS) {
+    float* a = s_act + tid * rw + net.w_off;
+    float sum = 0.f;
+    for (int j = 0; j <= M; ++j) {
+      a[j] = sigmoidf_(a[j]);
+      sum += a[j];
+    }
+    sum += 1e-10f;
+    for (int j = 0; j <= M; ++j) a[j] = a[j] / sum;
+  }
+  __syncthreads();
+  // every ray gathers the row of its image (each CTA serves the rays of its own images)
+  const int nr = 3 * M, nc = M + 1;
+  for (int64_t t = tid; t < N * nr; t += MOTION_THREADS) {
+    int64_t n = t / nr;
+    int j = (int)(t - n * nr);
+    int r = (int)(idx[n] - row0);
+    if (r >= 0 && r < nrows) {
+      out_r[t] = s_act[r * rw + net.r_off + j];
+      out_v[t] = s_act[r * rw + net.v_off + j];
+    }
+  }
+  for (int64_t t = tid; t < N * nc; t += MOTION_THREADS) {
+    int64_t n = t / nc;
+    int j = (int)(t - n * nc);
+    int r = (int)(idx[n] - row0);
+    if (r >= 0 && r < nrows) out_ccw[t] = s_act[r * rw + net.w_off + j];
+  }
+}
+
+__global__ void __launch_bounds__(MOTION_THREADS)
+motion_bwd_kernel(const __grid_constant__ lush_motion_net net, int n_img, const int64_t* __restrict__ idx,
+                  int64_t N, const float* __restrict__ rows, const float* __restrict__ g_r,
+                  const float* __restrict__ g_v, const float* __restrict__ g_ccw,
+                  float* __restrict__ g_embed) {
+  extern __shared__ float s_mem[];
+  const int rw = net.row_width, C = net.embed_dim, M = net.num_motion;
+  float* s_act = s_mem;                                 // [MOTION_ROWS][rw]
+  float* s_g = s_mem + MOTION_ROWS * rw;                // [MOTION_ROWS][rw]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MOTION_THREADS / 32;
+  const int row0 = blockIdx.x * MOTION_ROWS;
+  const int nrows = min(MOTION_ROWS, n_img - row0);
+  motion_prefetch_weights(net, tid);
+  for (int t = tid; t < MOTION_ROWS * rw; t += MOTION_THREADS) {
+    s_act[t] = t < nrows * rw ? rows[(int64_t)row0 * rw + t] : 0.f;
+    s_g[t] = 0.f;
+  }
+  __syncthreads();
+  // per-image sums of the per-ray gradients (shared-memory atomics; lanes of a warp hit different channels)
+  const int nr = 3 * M, nc = M + 1;
+  for (int64_t t = tid; t < N * nr; t += MOTION_THREADS) {
+    int64_t n = t / nr;
+    int j = (int)(t - n * nr);
+    int r = (int)(idx[n] - row0);
+    if (r >= 0 && r < nrows) {
+      if (g_r) atomicAdd(&s_g[r * rw + net.r_off + j], g_r[t]);
+      if (g_v) atomicAdd(&s_g[r * rw + net.v_off + j], g_v[t]);
+    }
+  }
+  if (g_ccw)
+    for (int64_t t = tid; t < N * nc; t += MOTION_THREADS) {
+      int64_t n = t / nc;
+      int j = (int)(t - n * nc);
+      int r = (int)(idx[n] - row0);
+      if (r >= 0 && r < nrows) atomicAdd(&s_g[r * rw + net.w_off + j], g_ccw[t]);
+    }
+  __syncthreads();
+  // heads backward
+  for (int t = tid; t < MOTION_ROWS * 6 * M; t += MOTION_THREADS) {
+    int r = t / (6 * M), j = t - r * 6 * M;
+    int off = j < 3 * M ? net.r_off + j : net.v_off + (j - 3 * M);
+    s_g[r * rw + off] *= net.rv_window;
+  }
+  if (tid < MOTION_ROWS) {
+    const float* a = s_act + tid * rw + net.w_off;
+    float* g = s_g + tid * rw + net.w_off;
+    float sum = 1e-10f, dot = 0.f;
+    for (int j = 0; j <= M; ++j) {
+      float w = sigmoidf_(a[j]);
+      sum += w;
+      dot += g[j] * w;
+    }
+    for (int j = 0; j <= M; ++j) {
+      float w = sigmoidf_(a[j]);
+      float gw = g[j] / sum - dot / (sum * sum);
+      g[j] = gw * w * (1.f - w);
+    }
+  }
+  __syncthreads();
+  for (int l = net.n_layers - 1; l >= 0; --l) {
+    const lush_dense_layer& L = net.layers[l];
+    const int in_dim = L.in0_dim + L.in1_dim;
+    if (L.act) {
+      for (int t = tid; t < MOTION_ROWS * L.out_dim; t += MOTION_THREADS) {
+        int r = t / L.out_dim, o = t - r * L.out_dim;
+        if (s_act[r * rw + L.out_off + o] <= 0.f) s_g[r * rw + L.out_off + o] = 0.f;
+      }
+      __syncthreads();
+    }
+    // weight / bias gradients: warp per output unit, lanes over its fan-in (coalesced reductions into global)
+    for (int o = warp; o < L.out_dim; o += nwarps) {
+      float g[MOTION_ROWS], gsum = 0.f;
+#pragma unroll
+      for (int r = 0; r < MOTION_ROWS; ++r) {
+        g[r] = s_g[r * rw + L.out_off + o];
+        gsum += g[r];
+      }
+      float* gwrow = L.gw + (int64_t)o * in_dim;
+      for (int k = lane; k < in_dim; k += 32) {
+        const float* a = s_act + motion_src(L, k);
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < MOTION_ROWS; ++r) s = fmaf(g[r], a[r * rw], s);
+        atomicAdd(&gwrow[k], s);
+      }
+      if (lane == 0) atomicAdd(&L.gb[o], gsum);
+    }
+    // input gradients: thread per input column, output units split over the thread groups
+    if (l > 0 || g_embed) {
+      const int groups = max(1, MOTION_THREADS / in_dim);
+      for (int k = tid % in_dim, og = tid / in_dim; og < groups && k < in_dim; k += MOTION_THREADS) {
+        float acc[MOTION_ROWS];
+#pragma unroll
+        for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = 0.f;
+        for (int o = og; o < L.out_dim; o += groups) {
+          float w = L.w[(int64_t)o * in_dim + k];
+          const float* g = s_g + L.out_off + o;
+#pragma unroll
+          for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = fmaf(w, g[r * rw], acc[r]);
+        }
+        int src = motion_src(L, k);
+#pragma unroll
+        for (int r = 0; r < MOTION_ROWS; ++r) atomicAdd(&s_g[r * rw + src], acc[r]);
+      }
+    }
+    __syncthreads();
+  }
+  if (g_embed)
+    for (int t = tid; t < nrows * C; t += MOTION_THREADS) {
+      int r = t / C, k = t - r * C;
+      g_embed[(int64_t)(row0 + r) * C + k] = s_g[r * rw + k];
+    }
+}
+
+static int motion_check(const lush_motion_net* net, const char* who) {
+  LUSH_REQUIRE(net && net->n_layers >= 1 && net->n_layers <= LUSH_MOTION_MAX_LAYERS, "%s: bad layer count", who);
+  LUSH_REQUIRE(net->embed_dim >= 1 && net->num_motion >= 1 && net->row_width >= net->embed_dim,
+               "%s: bad network dimensions", who);
+  const int rw = net->row_width, M = net->num_motion;
+  for (int l = 0; l < net->n_layers; ++l) {
+    const lush_dense_layer& L = net->layers[l];
+    LUSH_REQUIRE(L.w && L.b && L.in0_dim >= 1 && L.in1_dim >= 0 && L.out_dim >= 1, "%s: layer %d incomplete", who, l);
+    LUSH_REQUIRE(L.in0_off >= 0 && L.in0_off + L.in0_dim <= rw && L.out_off >= net->embed_dim &&
+                     L.out_off + L.out_dim <= rw && (L.in1_dim == 0 || (L.in1_off >= 0 && L.in1_off + L.in1_dim <= rw)),
+                 "%s: layer %d reads or writes outside the activation row", who, l);
+    LUSH_REQUIRE(L.in0_off + L.in0_dim <= L.out_off && (L.in1_dim == 0 || L.in1_off + L.in1_dim <= L.out_off),
+                 "%s: layer %d must read columns that precede its output", who, l);
+  }
+  LUSH_REQUIRE(net->r_off >= 0 && net->r_off + 3 * M <= rw && net->v_off >= 0 && net->v_off + 3 * M <= rw &&
+                   net->w_off >= 0 && net->w_off + M + 1 <= rw,
+               "%s: head offsets outside the activation row", who);
+  return 0;
+}
+
+}  // namespace lush
+
+using namespace lush;
+
+extern "C" int lush_rbk_motion_fwd(const lush_motion_net* net, const float* embed, int n_img,
+                                   const int64_t* images_idx, int64_t N, float* rows, float* r, float* v,
+                                   float* ccw, void* stream) {
+  int rc = motion_check(net, "rbk_motion_fwd");
+  if (rc) return rc;
+  LUSH_REQUIRE(embed && n_img >= 1 && N >= 0 && rows && (N == 0 || (images_idx && r && v && ccw)),
+               "rbk_motion_fwd: bad arguments");
+  size_t smem = (size_t)MOTION_ROWS * net->row_width * sizeof(float);
+  LUSH_REQUIRE(smem <= 200 * 1024, "rbk_motion_fwd: activation row of %d floats does not fit shared memory",
+               net->row_width);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(motion_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    LUSH_REQUIRE(e == cudaSuccess, "rbk_motion_fwd: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  unsigned blocks = (unsigned)ceil_div(n_img, MOTION_ROWS);
+  motion_fwd_kernel<<<blocks, MOTION_THREADS, smem, (cudaStream_t)stream>>>(*net, embed, n_img, images_idx, N, rows,
+                                                                            r, v, ccw);
+  LUSH_LAUNCH_CHECK("rbk_motion_fwd");
+  return 0;
+}
+
+extern "C" int lush_rbk_motion_bwd(const lush_motion_net* net, int n_img, const int64_t* images_idx, int64_t N,
+                                   const float* rows, const float* g_r, const float* g_v, const float* g_ccw,
+                                   float* g_embed, void* stream) {
+  int rc = motion_check(net, "rbk_motion_bwd");
+  if (rc) return rc;
+  LUSH_REQUIRE(n_img >= 1 && N >= 0 && rows && (N == 0 || images_idx), "rbk_motion_bwd: bad arguments");
+  for (int l = 0; l < net->n_layers; ++l)
+    LUSH_REQUIRE(net->layers[l].gw && net->layers[l].gb, "rbk_motion_bwd: layer %d has no gradient buffers", l);
+  size_t smem = (size_t)2 * MOTION_ROWS * net->row_width * sizeof(float);
+  LUSH_REQUIRE(smem <= 200 * 1024, "rbk_motion_bwd: activation row of %d floats does not fit shared memory",
+               net->row_width);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(motion_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    LUSH_REQUIRE(e == cudaSuccess, "rbk_motion_bwd: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  unsigned blocks = (unsigned)ceil_div(n_img, MOTION_ROWS);
+  motion_bwd_kernel<<<blocks, MOTION_THREADS, smem, (cudaStream_t)stream>>>(*net, n_img, images_idx, N, rows, g_r,
+                                                                            g_v, g_ccw, g_embed);
+  LUSH_LAUNCH_CHECK("rbk_motion_bwd");
+  return 0;
+}

@@ -112,17 +112,55 @@ class Rigid_Blurring_Kernel(nn.Module):
         w = torch.sigmoid(self.w_linear(hw))
         return r, v, w / (torch.sum(w, dim=-1, keepdims=True) + 1e-10)
 
-    def motion_params(self, rays_info):
-        """The motion parameters are a function of the image index alone, so when the table has fewer rows than
-        the batch the MLP runs once per IMAGE (num_img rows instead of N_rand) and the rays gather their image's
-        row; row-wise identical to the reference's per-ray evaluation (:118-153), 50x less work at 20 views."""
-        idx = rays_info['images_idx'].squeeze(-1)
+    def _motion_plan(self):
+        """Layer program of the fused motion kernel, or None when the topology is outside what it covers."""
         table = getattr(self.view_embedding_layer, 'view_embed_layer', None)
-        if isinstance(table, nn.Embedding) and table.num_embeddings <= idx.numel() and table.max_norm is None:
-            r, v, w = self._motion_mlp(table.weight)
-            nr, nv = r.shape[-1], v.shape[-1]
-            per_ray = torch.cat([r, v, w], -1).index_select(0, idx.reshape(-1))
-            return per_ray[:, :nr], per_ray[:, nr:nr + nv], per_ray[:, nr + nv:]
+        if not isinstance(table, nn.Embedding) or table.max_norm is not None or table.embedding_dim != self.input_ch:
+            return None
+        linears = [*self.view_embed_linears, *self.r_branch, self.r_linear, *self.v_branch, self.v_linear,
+                   *self.w_branch, self.w_linear]
+        cached = self.__dict__.get('_plan_cache')
+        if cached is not None and len(cached[0]) == len(linears) and \
+                all(w is l.weight and b is l.bias for (w, b), l in zip(cached[0], linears)):
+            return cached[1]
+        plan = self._build_motion_plan()
+        self.__dict__['_plan_cache'] = ([(l.weight, l.bias) for l in linears], plan)
+        return plan
+
+    def _build_motion_plan(self):
+        try:
+            plan = ops.MotionPlan(self.input_ch, self.num_motion, self.rv_window)
+            e = [(0, self.input_ch)]
+            h = e
+            for i, l in enumerate(self.view_embed_linears):
+                h = [plan.add(l, h, True)]
+                if i in self.skips:
+                    h = e + h
+            for name, stack, head in (("r", self.r_branch, self.r_linear), ("v", self.v_branch, self.v_linear),
+                                      ("w", self.w_branch, self.w_linear)):
+                hb = h
+                for l in stack:
+                    hb = [plan.add(l, hb, True)]
+                plan.add(head, hb, False)
+                plan.heads[name] = len(plan.layers) - 1
+            if (self.r_linear.out_features, self.v_linear.out_features, self.w_linear.out_features) != \
+                    (3 * self.num_motion, 3 * self.num_motion, self.num_motion + 1):
+                return None
+            if 8 * 2 * 4 * plan.width > 200 * 1024:
+                return None
+            return plan
+        except ValueError:
+            return None
+
+    def motion_params(self, rays_info):
+        """(r, v, ccw) of every ray (reference :118-147).  The motion parameters are a function of the image
+        index alone: the fused kernel evaluates the network once per IMAGE and the rays gather their image's row
+        (csrc/motion.cu).  `_motion_mlp` is the same computation with torch ops on the gathered embeddings; it
+        is what the kernel is tested against and what runs for a topology the kernel does not cover."""
+        idx = rays_info['images_idx'].squeeze(-1)
+        plan = self._motion_plan() if idx.is_cuda and os.environ.get("LUSH_FUSED_MOTION", "1") != "0" else None
+        if plan is not None:
+            return ops.rbk_motion(idx, plan, self.view_embedding_layer.view_embed_layer.weight, plan.params)
         return self._motion_mlp(self.view_embedding_layer(idx))
 
     def forward(self, rays, rays_info):

@@ -114,6 +114,7 @@ class _Composite(torch.autograd.Function):
               "lush_composite_fwd")
         ctx.save_for_backward(raw, z, rays_d, sigma_noise)
         ctx.meta = (float(thresh), int(bool(white_bkgd)), d_stride)
+        ctx.set_materialize_grads(False)     # unused outputs arrive as None (NULL for the kernel), not as zero fills
         return rgb, dens, acc, w, depth
 
     @staticmethod
@@ -294,6 +295,94 @@ def rbk_warp(rays, r, v):
 
 
 # ------------------------------------------------------------------------------------------------
+# motion-parameter network of the blur kernel (reference models/lushnerf.py:118-147), one launch each way
+# ------------------------------------------------------------------------------------------------
+class MotionPlan:
+    """Host description of the network for lush_rbk_motion_{fwd,bwd}: `layers` is a list of
+    (weight, bias, [(col_off, dim), ...] inputs, relu) in execution order; outputs are appended to the
+    activation row after the embedding columns.  heads = indices of the r, v, w head layers."""
+
+    def __init__(self, embed_dim, num_motion, rv_window):
+        self.embed_dim, self.num_motion, self.rv_window = int(embed_dim), int(num_motion), float(rv_window)
+        self.width = self.embed_dim
+        self.layers, self.params = [], []
+        self.heads = {}
+
+    def add(self, linear, inputs, relu):
+        """inputs: list of (col_off, dim) segments (at most two, concat order); returns the output segment."""
+        if len(inputs) not in (1, 2) or len(self.layers) >= _lib.MOTION_MAX_LAYERS:
+            raise ValueError("motion network: unsupported topology")
+        out_dim, in_dim = linear.weight.shape
+        if in_dim != sum(d for _, d in inputs) or linear.bias is None:
+            raise ValueError("motion network: layer shape does not match its inputs")
+        seg = (self.width, out_dim)
+        self.layers.append((inputs, seg, bool(relu)))
+        self.params += [linear.weight, linear.bias]
+        self.width += out_dim
+        return seg
+
+    def net(self, params, grads=None):
+        net = _lib.MotionNet()
+        net.n_layers, net.row_width, net.embed_dim = len(self.layers), self.width, self.embed_dim
+        net.num_motion, net.rv_window = self.num_motion, self.rv_window
+        net.r_off, net.v_off, net.w_off = (self.layers[self.heads[k]][1][0] for k in ("r", "v", "w"))
+        for i, (inputs, seg, relu) in enumerate(self.layers):
+            L = net.layers[i]
+            L.w, L.b = ptr(params[2 * i], "weight").value, ptr(params[2 * i + 1], "bias").value
+            if grads is not None:
+                L.gw, L.gb = grads[2 * i].data_ptr(), grads[2 * i + 1].data_ptr()
+            L.in0_off, L.in0_dim = inputs[0]
+            L.in1_off, L.in1_dim = inputs[1] if len(inputs) == 2 else (0, 0)
+            L.out_off, L.out_dim = seg
+            L.act = int(relu)
+        return net
+
+
+class _RbkMotion(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, plan, embed, *params):
+        idx = idx.reshape(-1).contiguous()
+        embed = _f32c(embed)
+        params = [_f32c(p) for p in params]
+        N, n_img, M = idx.numel(), embed.shape[0], plan.num_motion
+        rows = _empty((n_img, plan.width), embed)
+        r, v, ccw = _empty((N, 3 * M), embed), _empty((N, 3 * M), embed), _empty((N, M + 1), embed)
+        net = plan.net(params)
+        check(lib().lush_rbk_motion_fwd(byref(net), ptr(embed, "embedding"), n_img, ptr(idx, "images_idx", torch.int64),
+                                        N, ptr(rows), ptr(r), ptr(v), ptr(ccw), stream()), "lush_rbk_motion_fwd")
+        ctx.save_for_backward(idx, rows, embed, *params)
+        ctx.plan = plan
+        ctx.set_materialize_grads(False)
+        return r, v, ccw
+
+    @staticmethod
+    def backward(ctx, g_r, g_v, g_ccw):
+        idx, rows, embed, *params = ctx.saved_tensors
+        plan = ctx.plan
+        numels = [p.numel() for p in params]
+        flat = torch.zeros(sum(numels) + embed.numel(), dtype=torch.float32, device=embed.device)  # one fill
+        grads, off = [], 0
+        for p, n in zip(params, numels):
+            grads.append(flat[off:off + n].view(p.shape))
+            off += n
+        g_embed = flat[off:].view(embed.shape)
+        net = plan.net(params, grads)
+        check(lib().lush_rbk_motion_bwd(byref(net), embed.shape[0], ptr(idx, "images_idx", torch.int64), idx.numel(),
+                                        ptr(rows), ptr(_f32c(g_r)), ptr(_f32c(g_v)), ptr(_f32c(g_ccw)),
+                                        ptr(g_embed), stream()), "lush_rbk_motion_bwd")
+        need = ctx.needs_input_grad
+        return (None, None, g_embed if need[2] else None,
+                *[g if nd else None for g, nd in zip(grads, need[3:])])
+
+
+def rbk_motion(images_idx, plan: MotionPlan, embed_weight, params):
+    """(r [N,3M], v [N,3M], ccw [N,M+1]) for the rays' image indices; one kernel forward, one backward."""
+    if not embed_weight.is_cuda:
+        raise RuntimeError("lush_nerf_b200.rbk_motion needs CUDA tensors; there is no CPU fallback")
+    return _RbkMotion.apply(images_idx, plan, embed_weight, *params)
+
+
+# ------------------------------------------------------------------------------------------------
 # K-ray blend + noise + tone map (reference models/lushnerf.py:100-116, 649-654; helpers:164-174)
 # ------------------------------------------------------------------------------------------------
 class _BlendTonemap(torch.autograd.Function):
@@ -307,6 +396,7 @@ class _BlendTonemap(torch.autograd.Function):
                                            ptr(nz), N, K, int(bool(gamma)), stream()), "lush_blend_tonemap_fwd")
         ctx.save_for_backward(rgb, ccw, noise_raw)
         ctx.meta = (N, K, int(bool(gamma)))
+        ctx.set_materialize_grads(False)
         if nz is None:
             nz = torch.zeros_like(blur)
             ctx.mark_non_differentiable(nz)

@@ -256,9 +256,16 @@ int lush_tc_selftest(const void* a_blob, const void* b_blob, float* d_out, int N
  * tcgen05.mma M=128 K=16 from one thread; out_cycles[0] = issue cycles, out_cycles[1] = cycles to completion.
  * flags (per block of 8 MMAs): 1 = tcgen05.commit, 2 = tcgen05.fence::after_thread_sync, 4 = mbarrier wait. */
 int lush_tc_microbench(long long* out_cycles, int N, int nacc, int a_tmem, int iters, int flags, void* stream);
-/* Debug: copy the forward chain kernel's timeline trace (LUSH_CHAIN_DEBUG=2; clock64 stamps of CTA 0, third tile,
+/* Diagnostics: every CTA streams the same nblocks x block_bytes image from L2 through a 3-stage shared-memory ring
+ * `iters` times, unicast (cluster = 1) or with each CTA of a cluster fetching 1/cluster of a block and multicasting
+ * it (cluster = 2, 4).  out_cycles[grid] = cycles per CTA.  Measures the weight-delivery rate of the chain kernels. */
+int lush_tc_bcast_bench(const void* src, int nblocks, int block_bytes, int iters, int cluster, int grid,
+                        long long* out_cycles, void* stream);
+
+/* Debug (library built with -DLUSH_CHAIN_TRACE): copy the forward chain kernel's timeline trace (LUSH_CHAIN_DEBUG=2; clock64 stamps of CTA 0, third tile,
  * slot = step*16 + event) to host memory. */
 int lush_debug_read_chain_trace(long long* host_out, int n);
+int lush_debug_read_chain_trace_bwd(long long* host_out, int n);   /* same for the dgrad chain kernel */
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
           "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("LUSH_CHAIN_TRACE", "0") not in ("", "0"):
+    COMMON.append("-DLUSH_CHAIN_TRACE")      # timeline probes of the chain kernels (tools/trace_chain.py); use --force
 # per-file extra flags: the scan / sampler / ray kernels follow the reference's unfused fp32 op
 # sequence (bit-exact sample_pdf indices), so FMA contraction is disabled there.
 EXTRA = {

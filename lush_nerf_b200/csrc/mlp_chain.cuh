@@ -36,8 +36,24 @@
 namespace lush {
 
 constexpr int CH_THREADS = 512;
-constexpr int CH_NSTAGE = 3;
-constexpr int CH_STAGE_BYTES = 256 * (64 + 16) * 2;   // 40 KB: [256 x 64] weight block + [256 x 16] bias block
+constexpr int CH_MAX_NSTAGE = 4;
+// Weight ring, chosen per kernel (template parameter R of the producer / issuer):
+//   forward: 3 stages x 40 KB -- a [256 x 64] weight block + the [256 x 16] bias block ride in one stage
+//   dgrad:   4 stages x 32 KB -- no bias slices on the trunk steps and ~30 KB of spare shared memory: with as many
+//            stages as blocks per step, block j of a step reuses the stage of block j of the PREVIOUS step, so every
+//            copy is requested a whole step ahead (the copies take ~3 000 cycles under load; with 3 stages the last
+//            block of every step arrived ~2 000 cycles after its activations were ready)
+template <int NSTAGE_, int STAGE_BYTES_>
+struct ChRing {
+  static constexpr int NSTAGE = NSTAGE_;
+  static constexpr int STAGE_BYTES = STAGE_BYTES_;
+  static constexpr int STAGE0 = 0;
+  static constexpr int ACT = STAGE0 + NSTAGE_ * STAGE_BYTES_;        // [128 x 256] activations (A operand)
+  static constexpr int FREE0 = ACT + 128 * 256 * 2;                  // kernel-specific operands from here (see ChainMap)
+  static_assert(NSTAGE_ >= 2 && NSTAGE_ <= CH_MAX_NSTAGE, "ring depth");
+};
+using FwdRing = ChRing<3, 256 * (64 + 16) * 2>;
+using DgradRing = ChRing<4, 256 * 64 * 2>;
 constexpr int CH_MAX_STEPS = kMaxDepth + 6;
 constexpr int CH_WG_PRO = 0;                   // first warp of the prologue warpgroup
 constexpr int CH_WG_EPI0 = 4;                  // first warp of epilogue warpgroup 0
@@ -45,11 +61,6 @@ constexpr int CH_WARP_PRODUCER = 12;
 constexpr int CH_WARP_MMA0 = 14;               // issuer of even blocks (odd blocks: CH_WARP_MMA0 + 1)
 constexpr int CH_X16_BYTES = TROWS * 16 * 2;   // [128 x 16] fp16 tile
 
-struct ChSmem {
-  static constexpr int STAGE0 = 0;
-  static constexpr int ACT = STAGE0 + CH_NSTAGE * CH_STAGE_BYTES;    // [128 x 256] activations (A operand)
-  static constexpr int FREE0 = ACT + H_BYTES;                        // kernel-specific operands from here (see ChainMap)
-};
 // byte offsets of the kernel-specific shared-memory operands (strides: per tile parity b; 0 = single buffer)
 struct ChainMap {
   uint32_t enc, encv, encv_stride, x16, x16_stride;
@@ -59,8 +70,8 @@ struct ChainMap {
 // (bias ones / head gradients), optional K=32 slices against an encoding tile, and h_slices K=32 slices against
 // the activation tile (h_slices is even).
 // Weight stream per step: [pre16 block N x 16][enc block N x 32*enc_slices][hidden blocks N x 64 ...], each in
-// the tile-canonical layout with N rows.  Ring block 0 of a step = pre16 + enc (+ the first hidden block unless
-// enc_slices == 2); every further hidden block is one ring block.
+// the tile-canonical layout with N rows.  Ring block 0 of a step = pre16 + enc (+ the first hidden block when
+// enc_slices < 2 and the sum fits one ring stage); every further hidden block is one ring block.
 struct ChainStep {
   int16_t N;          // output columns (256 | 128 | 64)
   int8_t pre16;       // 0 | 1
@@ -83,32 +94,47 @@ struct ChainPlan {
   ChainStep steps[CH_MAX_STEPS];
 };
 
-__host__ __device__ inline int chain_merge_h0(const ChainStep& s) { return (s.enc_slices < 2 && s.h_slices > 0) ? 1 : 0; }
-__host__ __device__ inline int chain_block0_bytes(const ChainStep& s) {
-  return s.N * 2 * (16 * s.pre16 + KS * s.enc_slices + 64 * chain_merge_h0(s));
+__host__ __device__ inline int chain_merge_h0(const ChainStep& s, int stage_bytes) {
+  return (s.enc_slices < 2 && s.h_slices > 0 && s.N * 2 * (16 * s.pre16 + KS * s.enc_slices + 64) <= stage_bytes) ? 1 : 0;
 }
-__host__ __device__ inline int chain_nblocks(const ChainStep& s) { return 1 + (s.h_slices >> 1) - chain_merge_h0(s); }
+__host__ __device__ inline int chain_block0_bytes(const ChainStep& s, int stage_bytes) {
+  return s.N * 2 * (16 * s.pre16 + KS * s.enc_slices + 64 * chain_merge_h0(s, stage_bytes));
+}
+__host__ __device__ inline int chain_nblocks(const ChainStep& s, int stage_bytes) {
+  return 1 + (s.h_slices >> 1) - chain_merge_h0(s, stage_bytes);
+}
 __host__ __device__ inline int chain_step_bytes(const ChainStep& s) {
   return s.N * 2 * (16 * s.pre16 + KS * (s.enc_slices + s.h_slices));
 }
-static inline void chain_finish_plan(ChainPlan& P) {
+// returns false if a ring block of the plan does not fit one stage of the kernel's ring
+static inline bool chain_finish_plan(ChainPlan& P, int stage_bytes) {
   const char* dbg = getenv("LUSH_CHAIN_DEBUG");
   P.debug = dbg ? atoi(dbg) : 0;
   int64_t b = 0;
-  for (int s = 0; s < P.nsteps; ++s) b += chain_step_bytes(P.steps[s]);
+  bool fits = true;
+  for (int s = 0; s < P.nsteps; ++s) {
+    b += chain_step_bytes(P.steps[s]);
+    fits = fits && chain_block0_bytes(P.steps[s], stage_bytes) <= stage_bytes && P.steps[s].N * 64 * 2 <= stage_bytes;
+  }
   P.stream_bytes = b;
+  return fits;
 }
 
 // ---- optional timeline trace (LUSH_CHAIN_DEBUG bit 1): CTA 0 records clock64() of its third tile's events
 //   slot = step*16 + {0,1: issuer 0 start/end; 2,3: issuer 1; 4 + 4*g + {0: d_ready seen, 1: accumulator released,
-//   2,3: round 0 / round 1 published} for epilogue warpgroup g}
+//   2,3: round 2g / round 2g+1 published} for epilogue warpgroup g; 12..15: the step's last weight block: issuer
+//   reaches it, weights landed, activation group ready, MMAs issued}
+// The probes sit on the epilogue's critical path (~4 % of the forward kernel), so they are compiled in only with
+// -DLUSH_CHAIN_TRACE (LUSH_CHAIN_TRACE=1 python -m lush_nerf_b200.build --force; tools/trace_chain.py).
 static __device__ long long g_chain_trace[CH_MAX_STEPS * 16];   // one copy per translation unit
 __device__ __forceinline__ void chain_trace(const ChainPlan& P, int64_t it, int step, int ev) {
+#ifdef LUSH_CHAIN_TRACE
   if ((P.debug & 2) && blockIdx.x == 0 && it == 2 && (threadIdx.x & 31) == 0) g_chain_trace[step * 16 + ev] = clock64();
+#endif
 }
 
 struct ChainBars {
-  uint64_t full[CH_NSTAGE], empty[CH_NSTAGE];
+  uint64_t full[CH_MAX_NSTAGE], empty[CH_MAX_NSTAGE];
   uint64_t a_ready[4];          // K-values [64j, 64j+64) of the activation tile are complete (8 warps)
   uint64_t d_ready[2];          // accumulator d complete (one commit per issuer)
   uint64_t d_free[2];           // accumulator d is in the epilogue warps' registers (8 warps)
@@ -120,7 +146,7 @@ struct ChainBars {
 };
 
 __device__ __forceinline__ void chain_init_bars(ChainBars& B) {
-  for (int s = 0; s < CH_NSTAGE; ++s) { mbar_init(&B.full[s], 1); mbar_init(&B.empty[s], 1); }
+  for (int s = 0; s < CH_MAX_NSTAGE; ++s) { mbar_init(&B.full[s], 1); mbar_init(&B.empty[s], 1); }
   for (int j = 0; j < 4; ++j) mbar_init(&B.a_ready[j], 8);
   for (int r = 0; r < 2; ++r) {
     mbar_init(&B.d_ready[r], 2); mbar_init(&B.d_free[r], 8);
@@ -133,6 +159,7 @@ __device__ __forceinline__ void chain_init_bars(ChainBars& B) {
 }
 
 // ---- warp 12, one lane: stream the packed weight blocks of every tile through the ring
+template <class R>
 __device__ __forceinline__ void chain_producer(ChainBars& B, uint8_t* smem, const uint8_t* __restrict__ wstream,
                                                const ChainPlan& P, int64_t ntiles) {
   int stage = 0; uint32_t phase = 0;
@@ -140,18 +167,18 @@ __device__ __forceinline__ void chain_producer(ChainBars& B, uint8_t* smem, cons
     const uint8_t* src = wstream;
     for (int s = 0; s < P.nsteps; ++s) {
       const ChainStep& S = P.steps[s];
-      const uint32_t first = (uint32_t)chain_block0_bytes(S), big = (uint32_t)S.N * 64 * 2;
-      const int nblk = chain_nblocks(S);
+      const uint32_t first = (uint32_t)chain_block0_bytes(S, R::STAGE_BYTES), big = (uint32_t)S.N * 64 * 2;
+      const int nblk = chain_nblocks(S, R::STAGE_BYTES);
       for (int j = 0; j < nblk; ++j) {
         const uint32_t bytes = j == 0 ? first : big;
         mbar_wait(&B.empty[stage], phase ^ 1);
         if (P.debug & 1) { mbar_arrive(&B.full[stage]); }
         else {
           mbar_arrive_expect_tx(&B.full[stage], bytes);
-          bulk_g2s(smem + ChSmem::STAGE0 + stage * CH_STAGE_BYTES, src, bytes, &B.full[stage]);
+          bulk_g2s(smem + R::STAGE0 + stage * R::STAGE_BYTES, src, bytes, &B.full[stage]);
         }
         src += bytes;
-        if (++stage == CH_NSTAGE) { stage = 0; phase ^= 1; }
+        if (++stage == R::NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -199,6 +226,7 @@ __device__ __forceinline__ bool elect_one() {
 
 // ---- warps 14 and 15 (all 32 lanes, converged): issuer `my` issues blocks my, my+2, ... of every step.
 // Both walk the same block sequence of the weight ring and skip each other's blocks.
+template <class R>
 __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, uint32_t tmem_base, const ChainPlan& P,
                                                  const ChainMap map, int64_t ntiles, const uint32_t my) {
   uint32_t stage = 0, phase = 0;
@@ -208,7 +236,7 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
   const uint32_t sbase = smem_u32(smem);
   const uint32_t hi128 = desc_hi(128u);
   constexpr uint32_t A_K16 = (2u * TROWS * 16u) >> 4;   // start-address units per 16 columns of a 128-row blob
-  const uint32_t act_lo = desc_lo(sbase + ChSmem::ACT, TROWS * 16u);
+  const uint32_t act_lo = desc_lo(sbase + R::ACT, TROWS * 16u);
   const uint32_t enc_lo = desc_lo(sbase + map.enc, TROWS * 16u);
   int64_t it = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -222,14 +250,14 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
       const uint32_t b_lbo = (uint32_t)S.N * 16u;
       const uint32_t B_K16 = (2u * b_lbo) >> 4;
       const uint32_t e_lo = S.enc_src ? encv_lo : enc_lo;
-      const uint32_t merge = (uint32_t)chain_merge_h0(S);
-      const uint32_t nblk = (uint32_t)chain_nblocks(S);
+      const uint32_t merge = (uint32_t)chain_merge_h0(S, R::STAGE_BYTES);
+      const uint32_t nblk = (uint32_t)chain_nblocks(S, R::STAGE_BYTES);
       const uint32_t tacc = tmem_base + acc_sel * 256u;
       uint32_t seen = 0;                 // activation groups whose completion this issuer has observed this step
       chain_trace(P, it, s, 2 * (int)my);
       for (uint32_t i = 0; i < nblk; ++i) {
         if ((i & 1u) != my) {                  // the other issuer's block
-          if (++stage == CH_NSTAGE) { stage = 0; phase ^= 1u; }
+          if (++stage == R::NSTAGE) { stage = 0; phase ^= 1u; }
           continue;
         }
         if (i == 0) {                          // overwrites accumulator acc_sel: its previous epilogue must have drained it
@@ -237,11 +265,15 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
         } else if (i == 1) {                   // must not overtake block 0 in the tensor pipe
           mbar_wait(&B.first_issued, tok_phase);
         }
+        const bool last_blk = (i + 1u == nblk);                // probes 12..15: the step's last block
+        if (last_blk) chain_trace(P, it, s, 12);
         mbar_wait(&B.full[stage], phase);
-        uint32_t b_lo = desc_lo(sbase + ChSmem::STAGE0 + stage * CH_STAGE_BYTES, b_lbo);
+        if (last_blk) chain_trace(P, it, s, 13);
+        uint32_t b_lo = desc_lo(sbase + R::STAGE0 + stage * R::STAGE_BYTES, b_lbo);
         const uint32_t grp = (i == 0) ? 0u : i - 1u + merge;   // activation group read by this block (if any)
         const bool has_h = (i > 0) || merge;
         if (has_h && S.wait_a) { mbar_wait(&B.a_ready[grp], a_par); seen |= (1u << grp); }
+        if (last_blk) chain_trace(P, it, s, 14);
         tc_fence_after();
         if (elect_one()) {
           uint32_t acc = (i == 0) ? 0u : 1u;
@@ -258,7 +290,8 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
             else if (S.free_enc == 2) umma_commit(&B.pro_free[b]);
           }
         }
-        if (++stage == CH_NSTAGE) { stage = 0; phase ^= 1u; }
+        if (last_blk) chain_trace(P, it, s, 15);
+        if (++stage == R::NSTAGE) { stage = 0; phase ^= 1u; }
       }
       // per-step bookkeeping (both issuers observe every barrier phase they track, in order)
       if (S.wait_a) {   // every writer publishes all four groups (a 128-wide one publishes 2 and 3 as empty)
@@ -281,13 +314,13 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
 __device__ __forceinline__ void chain_publish(ChainBars& B, int j, int lane) {
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) mbar_arrive(&B.a_ready[j]);
+  mbar_arrive_if(&B.a_ready[j], lane == 0);
 }
 // this warp's share of accumulator d is in registers
 __device__ __forceinline__ void chain_release_acc(ChainBars& B, int d, int lane) {
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(&B.d_free[d]);
+  mbar_arrive_if(&B.d_free[d], lane == 0);
 }
 
 }  // namespace lush

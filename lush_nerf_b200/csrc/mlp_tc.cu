@@ -48,12 +48,12 @@ static void make_fwd_chain(const MlpLayout& L, const FwdPlan& P, ChainPlan& C) {
     s.epi = FE_VIEWS; s.p0 = 0; s.p1 = 0; s.off0 = P.rec_hv; s.off1 = P.rec_maskv;
     ++n; }
   C.nsteps = n;
-  chain_finish_plan(C);
+  if (!chain_finish_plan(C, FwdRing::STAGE_BYTES)) C.nsteps = -1;   // rejected by the host entry point
 }
 
 // shared-memory map of the forward kernel behind the ring and the activation tile
 struct FwdSmem {
-  static constexpr int ENC = ChSmem::FREE0;                 // [128 x 64] gamma(x), single buffer
+  static constexpr int ENC = FwdRing::FREE0;                 // [128 x 64] gamma(x), single buffer
   static constexpr int ENCV = ENC + ENC_BYTES;              // 2 x [128 x 32] gamma(viewdirs)
   static constexpr int ONES = ENCV + 2 * ENCV_BYTES;        // [128 x 16], column 0 = 1 (bias operand)
   static constexpr int PARAMS = ONES + CH_X16_BYTES;        // head weights (fp32)
@@ -200,10 +200,10 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == CH_WARP_PRODUCER) {
-    if (lane == 0) chain_producer(B, smem, wstream, C, ntiles);
+    if (lane == 0) chain_producer<FwdRing>(B, smem, wstream, C, ntiles);
   } else if (warp >= CH_WARP_MMA0) {
     const ChainMap map = {(uint32_t)FwdSmem::ENC, (uint32_t)FwdSmem::ENCV, (uint32_t)ENCV_BYTES, (uint32_t)FwdSmem::ONES, 0u};
-    chain_mma_issuer(B, smem, tmem_base, C, map, ntiles, (uint32_t)(warp - CH_WARP_MMA0));
+    chain_mma_issuer<FwdRing>(B, smem, tmem_base, C, map, ntiles, (uint32_t)(warp - CH_WARP_MMA0));
   } else if (warp < CH_WG_EPI0) {
     // =========================== prologue warpgroup: sample points + encodings of the NEXT tile ===========
     const int row = tid - CH_WG_PRO * 32;
@@ -241,7 +241,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
     const int row = 32 * (warp & 3) + lane;           // TMEM lane == tile row (a warp may only touch lanes 32*(warp%4)..)
     const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
     const bool tracer = (warp == CH_WG_EPI0 + 4 * g);
-    uint8_t* act = smem + ChSmem::ACT;
+    uint8_t* act = smem + FwdRing::ACT;
     const float4* wa4 = reinterpret_cast<const float4*>(sparams + P.w_alpha_off);
     const float4* wr4 = reinterpret_cast<const float4*>(sparams + P.w_rgb_off);
     uint32_t d_phase = 0, aux_phase = 0, acc_sel = 0;   // d_phase: bit per accumulator
@@ -282,11 +282,11 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                 *reinterpret_cast<uint4*>(act + ((col >> 3) + q) * (TROWS * 16) + row * 16) =
                     make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
               chain_publish(B, rd, lane);
-              if (tracer && rd < 2) chain_trace(C, it, s, 6 + 4 * g + rd);
+              if (tracer && (rd >> 1) == g) chain_trace(C, it, s, 6 + 4 * g + (rd & 1));
               if (TRAIN) {
                 store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
                 if (S_.epi != FE_FEATURE)
-                  *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (col >> 5) * 4) = sign_bits(r);
+                  *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd) * 4) = sign_bits(r);
               }
               if (S_.epi == FE_TRUNK_LAST) {
 #pragma unroll
@@ -312,7 +312,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               if (TRAIN) {
                 pack_chunk<true>(r, pw);
                 store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
-                *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (col >> 5) * 4) = sign_bits(r);
+                *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd) * 4) = sign_bits(r);
               }
             }
           }
@@ -413,6 +413,7 @@ int lush_mlp_tc_fwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
                "mlp_fwd(tc): unaligned buffers");
   ChainPlan C;
   make_fwd_chain(L, P, C);
+  LUSH_REQUIRE(C.nsteps > 0, "mlp_fwd(tc): a weight block of this topology does not fit the ring stage");
   __half* wstream = reinterpret_cast<__half*>(workspace);
   float* gparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((C.stream_bytes + 255) / 256) * 256);
   PackPlan K;

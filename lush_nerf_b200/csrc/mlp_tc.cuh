@@ -121,12 +121,24 @@ __host__ __device__ constexpr int relu_mask_pos(int c) {
 __host__ __device__ constexpr int relu_mask_col(int P) {
   return 2 * (2 * ((P & 15) < 8 ? 7 - (P & 15) : 15 - (P & 15)) + ((P & 15) < 8 ? 1 : 0)) + (P >> 4);
 }
-// sign bits of 32 fp32 accumulators in the layout above: 32 funnel shifts, the k-th shifted-in bit ends at 31-k
+// sign bits of 32 fp32 accumulators in the layout above: 32 funnel shifts, the k-th shifted-in bit ends at 31-k.
+// Four independent 8-shift chains (one per result byte) instead of one 32-deep dependency chain: the epilogue warps
+// are latency bound, not issue bound.
+__device__ __forceinline__ uint32_t shf_in1(uint32_t src, uint32_t acc) {   // (acc << 1) | sign(src)
+  uint32_t r;
+  asm("shf.l.wrap.b32 %0, %1, %2, 1;" : "=r"(r) : "r"(src), "r"(acc));
+  return r;
+}
 __device__ __forceinline__ uint32_t sign_bits(const uint32_t (&r)[32]) {
-  uint32_t mb = 0;
+  uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
-  for (int k = 0; k < 32; ++k) mb = __funnelshift_l(r[relu_mask_col(31 - k)], mb, 1);
-  return mb;
+  for (int j = 0; j < 8; ++j) {
+    m0 = shf_in1(r[relu_mask_col(31 - j)], m0);
+    m1 = shf_in1(r[relu_mask_col(23 - j)], m1);
+    m2 = shf_in1(r[relu_mask_col(15 - j)], m2);
+    m3 = shf_in1(r[relu_mask_col(7 - j)], m3);
+  }
+  return (m0 << 24) | (m1 << 16) | (m2 << 8) | m3;
 }
 // zero the fp16 lanes of packed word w (columns 2w, 2w+1 of the chunk) whose mask bit is set: shift + prmt + lop3
 template <int W_>

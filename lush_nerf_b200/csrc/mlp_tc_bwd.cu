@@ -84,7 +84,7 @@ static void make_bwd_chain(const MlpLayout& L, bool need_in, ChainPlan& C, BwdPl
   if (need_in) add(64, 0, 8, prev_wrote, 0, 0, BE_ENC, 1, 0, L.pts_w[0], L.pts_in[0], 0, L.in_ch, 0, 0);
   C.nsteps = n;
   K.njobs = n;
-  chain_finish_plan(C);
+  if (!chain_finish_plan(C, DgradRing::STAGE_BYTES)) C.nsteps = -1;   // rejected by the host entry point
 }
 
 // stream of a step: [pre16 block N x 16] [hidden blocks N x 64 ...]; element (n, k) = W[k][col0 + n]
@@ -142,13 +142,26 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
 
 // shared-memory map of the dgrad kernel behind the ring and the activation tile
 struct DgSmem {
-  static constexpr int G16 = ChSmem::FREE0;                 // 2 x [128 x 16]: (g_r, g_g, g_b, g_sigma, 0...) * scale
+  static constexpr int G16 = DgradRing::FREE0;                 // 2 x [128 x 16]: (g_r, g_g, g_b, g_sigma, 0...) * scale
   static constexpr int TOTAL = G16 + 2 * CH_X16_BYTES;
 };
 
 // ------------------------------------------------------------------------------------------------
 // stage 1: fused dgrad chain (one instance of the skeleton in mlp_chain.cuh)
 // ------------------------------------------------------------------------------------------------
+// ReLU mask words of `row` for the epilogue of one dgrad step: warpgroup g owns columns [64 rd + 32 g, +32) of every
+// round rd; the forward kernel stores a row's words as [g][rd], i.e. one aligned 16-byte (trunk) / 8-byte (views) load.
+__device__ __forceinline__ uint4 dgrad_mask_words(const uint8_t* frec, const FwdPlan& P, int epi, int p0, int row, int g) {
+  uint4 m = make_uint4(0u, 0u, 0u, 0u);
+  if (epi == BE_TRUNK) {
+    m = *reinterpret_cast<const uint4*>(frec + P.rec_mask + (p0 * TROWS + row) * 32 + g * 16);
+  } else if (epi == BE_VIEWS) {
+    const uint2 v = *reinterpret_cast<const uint2*>(frec + P.rec_maskv + row * 16 + g * 8);
+    m.x = v.x; m.y = v.y;
+  }
+  return m;
+}
+
 __global__ void __launch_bounds__(CH_THREADS, 1)
 mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ g_out,
                     const unsigned* __restrict__ scale_buf, const uint8_t* __restrict__ fstash,
@@ -171,10 +184,10 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == CH_WARP_PRODUCER) {
-    if (lane == 0) chain_producer(B, smem, bstream, C, ntiles);
+    if (lane == 0) chain_producer<DgradRing>(B, smem, bstream, C, ntiles);
   } else if (warp >= CH_WARP_MMA0) {
     const ChainMap map = {0u, 0u, 0u, (uint32_t)DgSmem::G16, (uint32_t)CH_X16_BYTES};
-    chain_mma_issuer(B, smem, tmem_base, C, map, ntiles, (uint32_t)(warp - CH_WARP_MMA0));
+    chain_mma_issuer<DgradRing>(B, smem, tmem_base, C, map, ntiles, (uint32_t)(warp - CH_WARP_MMA0));
   } else if (warp < CH_WG_EPI0) {
     // =========================== prologue warpgroup: loss-scaled head gradients of the NEXT tile ===========
     const int row = tid - CH_WG_PRO * 32;
@@ -196,26 +209,27 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
     const int g = (warp - CH_WG_EPI0) >> 2;
     const int row = 32 * (warp & 3) + lane;
     const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
-    uint8_t* act = smem + ChSmem::ACT;
+    uint8_t* act = smem + DgradRing::ACT;
     uint32_t d_phase = 0, acc_sel = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    uint4 mnext = make_uint4(0u, 0u, 0u, 0u);
+    if ((int64_t)blockIdx.x < ntiles)
+      mnext = dgrad_mask_words(fstash + blockIdx.x * (int64_t)P.rec_bytes, P, C.steps[0].epi, C.steps[0].p0, row, g);
+    const bool tracer = (warp == CH_WG_EPI0 + 4 * g);
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint8_t* frec = fstash + tile * (int64_t)P.rec_bytes;
       uint8_t* grec = gstash + tile * (int64_t)Bp.grec_bytes;
       for (int s = 0; s < C.nsteps; ++s, acc_sel ^= 1u) {
         const ChainStep S_ = C.steps[s];
         const int nround = S_.N >> 6;
-        // the ReLU bits of my columns (one word per round), fetched before waiting on the MMA
-        uint32_t mw[4] = {0u, 0u, 0u, 0u};
-        if (S_.epi == BE_TRUNK) {
-          const uint32_t* mp = reinterpret_cast<const uint32_t*>(frec + P.rec_mask + (S_.p0 * TROWS + row) * 32);
-#pragma unroll
-          for (int rd = 0; rd < 4; ++rd) mw[rd] = mp[2 * rd + g];
-        } else if (S_.epi == BE_VIEWS) {
-          const uint32_t* mp = reinterpret_cast<const uint32_t*>(frec + P.rec_maskv + row * 16);
-          mw[0] = mp[g]; mw[1] = mp[2 + g];
-        }
+        // the ReLU bits of my columns (one word per round) were requested one step ago (DRAM latency ~1 us)
+        const uint4 mq = mnext;
+        if (s + 1 < C.nsteps) mnext = dgrad_mask_words(frec, P, C.steps[s + 1].epi, C.steps[s + 1].p0, row, g);
+        else if (tile + gridDim.x < ntiles)
+          mnext = dgrad_mask_words(fstash + (tile + gridDim.x) * (int64_t)P.rec_bytes, P, C.steps[0].epi, C.steps[0].p0, row, g);
         mbar_wait(&B.d_ready[acc_sel], (d_phase >> acc_sel) & 1u); d_phase ^= (1u << acc_sel);
         tc_fence_after();
+        if (tracer) chain_trace(C, it, s, 4 + 4 * g);
         const uint32_t tacc = tmem_base + tlane + acc_sel * 256u + 32u * g;
         uint32_t ra[32], rb2[32], pw[16];
         tmem_ld32(tacc, ra);
@@ -229,10 +243,13 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
               const int col = 64 * rd + 32 * g;
               tmem_ld_wait();
               if (rd + 1 < nround) tmem_ld32(tacc + 64u * (rd + 1), hb ? ra : rb2);
-              else chain_release_acc(B, (int)acc_sel, lane);
+              else {
+                chain_release_acc(B, (int)acc_sel, lane);
+                if (tracer) chain_trace(C, it, s, 5 + 4 * g);
+              }
               pack_chunk<false>(r, pw);
               if (S_.epi == BE_TRUNK || S_.epi == BE_VIEWS) {   // ReLU gate of the producing layer
-                const uint32_t m = mw[rd];
+                const uint32_t m = rd2 == 0 ? (hb ? mq.y : mq.x) : (hb ? mq.w : mq.z);
                 pw[0] = relu_mask_apply<0>(pw[0], m);   pw[1] = relu_mask_apply<1>(pw[1], m);
                 pw[2] = relu_mask_apply<2>(pw[2], m);   pw[3] = relu_mask_apply<3>(pw[3], m);
                 pw[4] = relu_mask_apply<4>(pw[4], m);   pw[5] = relu_mask_apply<5>(pw[5], m);
@@ -249,6 +266,7 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
                     *reinterpret_cast<uint4*>(act + ((col >> 3) + q) * (TROWS * 16) + row * 16) =
                         make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
                   chain_publish(B, rd, lane);
+                  if (tracer && (rd >> 1) == g) chain_trace(C, it, s, 6 + 4 * g + (rd & 1));
                 }
                 store_chunk_global(grec + S_.off0, S_.N >> 3, col, row, pw);
               } else {
@@ -716,6 +734,7 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
   const bool need_in = g_ray_batch != nullptr;
   FwdPlan P; make_fwd_plan(L, P);
   ChainPlan C; BwdPlan B; BPackPlan K; make_bwd_chain(L, need_in, C, B, K);
+  LUSH_REQUIRE(C.nsteps > 0, "mlp_bwd(tc): a weight block of this topology does not fit the ring stage");
   const BwdWorkspace w = bwd_ws_layout(L, M, true);
   if (!workspace || workspace_bytes < w.total) {
     set_error("mlp_bwd(tc): workspace too small (%zu < %zu)", workspace_bytes, w.total);
@@ -782,4 +801,9 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
     LUSH_LAUNCH_CHECK("ray_grad_reduce");
   }
   return 0;
+}
+
+extern "C" int lush_debug_read_chain_trace_bwd(long long* host_out, int n) {   // dgrad kernel's trace (this translation unit)
+  LUSH_REQUIRE(host_out && n > 0 && n <= CH_MAX_STEPS * 16, "read_chain_trace_bwd: bad arguments");
+  return check_cuda(cudaMemcpyFromSymbol(host_out, g_chain_trace, sizeof(long long) * n), "read_chain_trace_bwd");
 }

@@ -197,3 +197,99 @@ extern "C" int lush_tc_microbench(long long* out_cycles, int N, int nacc, int a_
   LUSH_LAUNCH_CHECK("tc_microbench");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Microbenchmark: every CTA streams the SAME `nblocks` x `block_bytes` weight image from L2 into a 3-stage
+// shared-memory ring, `iters` times (the access pattern of the chain kernels' weight producer), either with
+// one unicast bulk copy per CTA and block, or -- clusters of CL CTAs -- with each CTA fetching 1/CL of a block
+// and multicasting it to the whole cluster.  out[cta] = cycles; tells whether multicast raises the delivered
+// weight bandwidth per SM.  Not on the product path.
+// ------------------------------------------------------------------------------------------------
+namespace lush {
+using namespace tc;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+               "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                            uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+
+template <int CL>
+__global__ void __launch_bounds__(128) bcast_bench_kernel(const uint8_t* __restrict__ src, int nblocks, int block_bytes,
+                                                          int iters, long long* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[3], empty[3];
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 3; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  long long t0 = clock64();
+  if (threadIdx.x == 0) {
+    // producer and consumer in one thread, software-pipelined 3 deep: issue block i, consume block i-2
+    const int total = nblocks * iters;
+    const uint32_t part = (uint32_t)block_bytes / CL;
+    int ps = 0, cs = 0; uint32_t pphase = 0, cphase = 0;
+    for (int i = 0; i < total + 2; ++i) {
+      if (i < total) {
+        if (i >= 3) mbar_wait(&empty[ps], pphase ^ 1);
+        mbar_arrive_expect_tx(&full[ps], (uint32_t)block_bytes);
+        const uint8_t* g = src + (size_t)(i % nblocks) * block_bytes + rank * part;
+        uint8_t* d = smem + ps * block_bytes + rank * part;
+        if (CL > 1) bulk_g2s_mc(d, g, part, &full[ps], (uint16_t)((1u << CL) - 1u));
+        else bulk_g2s(d, g, part, &full[ps]);
+        if (++ps == 3) { ps = 0; pphase ^= 1; }
+      }
+      if (i >= 2) {
+        mbar_wait(&full[cs], cphase);
+        if (CL > 1) { for (uint32_t c = 0; c < CL; ++c) mbar_arrive_remote(&empty[cs], c); }
+        else mbar_arrive(&empty[cs]);
+        if (++cs == 3) { cs = 0; cphase ^= 1; }
+      }
+    }
+  }
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
+}
+
+}  // namespace lush
+
+extern "C" int lush_tc_bcast_bench(const void* src, int nblocks, int block_bytes, int iters, int cluster, int grid,
+                                   long long* out_cycles, void* stream) {
+  using namespace lush;
+  LUSH_REQUIRE(src && out_cycles && nblocks > 0 && iters > 0 && block_bytes > 0 && block_bytes % 64 == 0 &&
+                   3 * block_bytes <= 200 * 1024 && (cluster == 1 || cluster == 2 || cluster == 4) && grid > 0 &&
+                   grid % cluster == 0,
+               "tc_bcast_bench: bad arguments");
+  void (*kern)(const uint8_t*, int, int, int, long long*) =
+      cluster == 1 ? bcast_bench_kernel<1> : cluster == 2 ? bcast_bench_kernel<2> : bcast_bench_kernel<4>;
+  const size_t smem = (size_t)3 * block_bytes;
+  LUSH_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
+               "tc_bcast_bench: cannot raise the shared memory limit");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  const uint8_t* s8 = (const uint8_t*)src;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, s8, nblocks, block_bytes, iters, out_cycles);
+  LUSH_REQUIRE(e == cudaSuccess, "tc_bcast_bench: launch failed: %s", cudaGetErrorString(e));
+  LUSH_LAUNCH_CHECK("tc_bcast_bench");
+  return 0;
+}

@@ -36,6 +36,9 @@ __device__ __forceinline__ void small_dense(int t, int N, const float* __restric
 #pragma unroll
     for (int r = 0; r < TM; ++r) acc[r] = b;
     const float* wrow = Wt + (int64_t)t * fan;
+    // every thread walks its own weight row: request all of its cache lines up front, so the walk pays one L2 round
+    // trip instead of one per 128 bytes
+    for (int k = 0; k < fan; k += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(wrow + k));
 #pragma unroll 1
     for (int seg = 0; seg < 2; ++seg) {
       const float* x = seg ? x1 : x0;

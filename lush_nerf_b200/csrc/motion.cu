@@ -14,9 +14,33 @@ namespace lush {
 
 constexpr int MOTION_ROWS = 8;
 constexpr int MOTION_THREADS = 512;
+constexpr int MOTION_CHUNK = 4096;       // rays whose image slot is staged in shared memory at a time
 
 __device__ __forceinline__ int motion_src(const lush_dense_layer& L, int k) {
   return k < L.in0_dim ? L.in0_off + k : L.in1_off + (k - L.in0_dim);
+}
+
+// Sums of 8 per-lane accumulators (one per row) over the warp in 9 shuffles instead of 40: the lanes trade halves of
+// their rows while they reduce (xor 16, 8, 4), then finish the one row they are left with (xor 2, 1).
+static_assert(MOTION_ROWS == 8, "motion_reduce_rows is written for 8 rows");
+__device__ __forceinline__ int motion_row_of(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+__device__ __forceinline__ float motion_reduce_rows(float (&acc)[MOTION_ROWS], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float send = h16 ? acc[r] : acc[r + 4], keep = h16 ? acc[r + 4] : acc[r];
+    acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float send = h8 ? acc[r] : acc[r + 2], keep = h8 ? acc[r + 2] : acc[r];
+    acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const float send = h4 ? acc[0] : acc[1], keep = h4 ? acc[1] : acc[0];
+  float v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
 }
 
 // Pull every weight matrix (~100 KB in all) towards L1 at kernel start: the layer loop then waits on L1 hits
@@ -35,6 +59,7 @@ motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __re
                   const int64_t* __restrict__ idx, int64_t N, float* __restrict__ rows,
                   float* __restrict__ out_r, float* __restrict__ out_v, float* __restrict__ out_ccw) {
   extern __shared__ float s_act[];                      // [MOTION_ROWS][rw]
+  __shared__ int s_slot[MOTION_CHUNK];
   const int rw = net.row_width, C = net.embed_dim, M = net.num_motion;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MOTION_THREADS / 32;
   const int row0 = blockIdx.x * MOTION_ROWS;
@@ -53,22 +78,15 @@ motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __re
 #pragma unroll
       for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = 0.f;
       const float* wrow = L.w + (int64_t)o * in_dim;
+#pragma unroll 2
       for (int k = lane; k < in_dim; k += 32) {
         float w = wrow[k];
         const float* a = s_act + motion_src(L, k);
 #pragma unroll
         for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = fmaf(w, a[r * rw], acc[r]);
       }
-      float mine = 0.f;
-#pragma unroll
-      for (int r = 0; r < MOTION_ROWS; ++r) {
-        float s = warp_sum(acc[r]);
-        if (lane == r) mine = s;
-      }
-      if (lane < MOTION_ROWS) {
-        mine += L.b[o];
-        s_act[lane * rw + L.out_off + o] = L.act ? fmaxf(mine, 0.f) : mine;
-      }
+      const float mine = motion_reduce_rows(acc, lane) + L.b[o];       // lane holds row motion_row_of(lane)
+      if ((lane & 3) == 0) s_act[motion_row_of(lane) * rw + L.out_off + o] = L.act ? fmaxf(mine, 0.f) : mine;
     }
     __syncthreads();
   }
@@ -92,22 +110,27 @@ motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __re
     for (int j = 0; j <= M; ++j) a[j] = a[j] / sum;
   }
   __syncthreads();
-  // every ray gathers the row of its image (each CTA serves the rays of its own images)
+  // every ray gathers the row of its image (each CTA serves the rays of its own images): the image slots of a chunk
+  // of rays are staged in shared memory first, so the copy loop has no dependent global load in it
   const int nr = 3 * M, nc = M + 1;
-  for (int64_t t = tid; t < N * nr; t += MOTION_THREADS) {
-    int64_t n = t / nr;
-    int j = (int)(t - n * nr);
-    int r = (int)(idx[n] - row0);
-    if (r >= 0 && r < nrows) {
-      out_r[t] = s_act[r * rw + net.r_off + j];
-      out_v[t] = s_act[r * rw + net.v_off + j];
+  for (int64_t n0 = 0; n0 < N; n0 += MOTION_CHUNK) {
+    const int cn = (int)min((int64_t)MOTION_CHUNK, N - n0);
+    __syncthreads();
+    for (int i = tid; i < cn; i += MOTION_THREADS) {
+      const int64_t r = idx[n0 + i] - row0;
+      s_slot[i] = (r >= 0 && r < nrows) ? (int)r : -1;
     }
-  }
-  for (int64_t t = tid; t < N * nc; t += MOTION_THREADS) {
-    int64_t n = t / nc;
-    int j = (int)(t - n * nc);
-    int r = (int)(idx[n] - row0);
-    if (r >= 0 && r < nrows) out_ccw[t] = s_act[r * rw + net.w_off + j];
+    __syncthreads();
+    for (int i = tid; i < cn; i += MOTION_THREADS) {
+      const int r = s_slot[i];
+      if (r < 0) continue;
+      const float* a = s_act + r * rw;
+      float* pr = out_r + (n0 + i) * nr;
+      float* pv = out_v + (n0 + i) * nr;
+      float* pc = out_ccw + (n0 + i) * nc;
+      for (int j = 0; j < nr; ++j) { pr[j] = a[net.r_off + j]; pv[j] = a[net.v_off + j]; }
+      for (int j = 0; j < nc; ++j) pc[j] = a[net.w_off + j];
+    }
   }
 }
 
@@ -117,6 +140,7 @@ motion_bwd_kernel(const __grid_constant__ lush_motion_net net, int n_img, const 
                   const float* __restrict__ g_v, const float* __restrict__ g_ccw,
                   float* __restrict__ g_embed) {
   extern __shared__ float s_mem[];
+  __shared__ int s_slot[MOTION_CHUNK];
   const int rw = net.row_width, C = net.embed_dim, M = net.num_motion;
   float* s_act = s_mem;                                 // [MOTION_ROWS][rw]
   float* s_g = s_mem + MOTION_ROWS * rw;                // [MOTION_ROWS][rw]
@@ -129,24 +153,35 @@ motion_bwd_kernel(const __grid_constant__ lush_motion_net net, int n_img, const 
     s_g[t] = 0.f;
   }
   __syncthreads();
-  // per-image sums of the per-ray gradients (shared-memory atomics; lanes of a warp hit different channels)
+  // per-image sums of the per-ray gradients: image slots staged per chunk of rays, then one thread per (ray, channel)
+  // with shared-memory atomics (the lanes of a warp hit different channels of at most a few rays)
   const int nr = 3 * M, nc = M + 1;
-  for (int64_t t = tid; t < N * nr; t += MOTION_THREADS) {
-    int64_t n = t / nr;
-    int j = (int)(t - n * nr);
-    int r = (int)(idx[n] - row0);
-    if (r >= 0 && r < nrows) {
-      if (g_r) atomicAdd(&s_g[r * rw + net.r_off + j], g_r[t]);
-      if (g_v) atomicAdd(&s_g[r * rw + net.v_off + j], g_v[t]);
+  for (int64_t n0 = 0; n0 < N; n0 += MOTION_CHUNK) {
+    const int cn = (int)min((int64_t)MOTION_CHUNK, N - n0);
+    __syncthreads();
+    for (int i = tid; i < cn; i += MOTION_THREADS) {
+      const int64_t r = idx[n0 + i] - row0;
+      s_slot[i] = (r >= 0 && r < nrows) ? (int)r : -1;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int t = tid; t < cn * nr; t += MOTION_THREADS) {
+      const int i = t / nr, j = t - i * nr;
+      const int r = s_slot[i];
+      if (r >= 0) {
+        if (g_r) atomicAdd(&s_g[r * rw + net.r_off + j], g_r[n0 * nr + t]);
+        if (g_v) atomicAdd(&s_g[r * rw + net.v_off + j], g_v[n0 * nr + t]);
+      }
+    }
+    if (g_ccw) {
+#pragma unroll 4
+      for (int t = tid; t < cn * nc; t += MOTION_THREADS) {
+        const int i = t / nc, j = t - i * nc;
+        const int r = s_slot[i];
+        if (r >= 0) atomicAdd(&s_g[r * rw + net.w_off + j], g_ccw[n0 * nc + t]);
+      }
     }
   }
-  if (g_ccw)
-    for (int64_t t = tid; t < N * nc; t += MOTION_THREADS) {
-      int64_t n = t / nc;
-      int j = (int)(t - n * nc);
-      int r = (int)(idx[n] - row0);
-      if (r >= 0 && r < nrows) atomicAdd(&s_g[r * rw + net.w_off + j], g_ccw[t]);
-    }
   __syncthreads();
   // heads backward
   for (int t = tid; t < MOTION_ROWS * 6 * M; t += MOTION_THREADS) {
@@ -205,6 +240,7 @@ motion_bwd_kernel(const __grid_constant__ lush_motion_net net, int n_img, const 
         float acc[MOTION_ROWS];
 #pragma unroll
         for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = 0.f;
+#pragma unroll 4
         for (int o = og; o < L.out_dim; o += groups) {
           float w = L.w[(int64_t)o * in_dim + k];
           const float* g = s_g + L.out_off + o;

@@ -22,7 +22,7 @@ rows = list(csv.reader(io.StringIO(src)))
 hi = next(i for i, r in enumerate(rows) if "Address" in r and "Source" in r)
 h = rows[hi]
 ai, si, wi, ii = h.index("Address"), h.index("Source"), h.index("Warp Stall Sampling (All Samples)"), h.index("Instructions Executed")
-data = [r for r in rows[hi + 1:] if len(r) == len(h)]
+data = [r for r in rows[hi + 1:] if len(r) == len(h) and (r[wi] or '0').isdigit()]   # the header repeats per kernel
 tot = sum(int(r[wi] or 0) for r in data)
 print("total samples", tot)
 for r in sorted(data, key=lambda r: -int(r[wi] or 0))[:ntop]:

@@ -50,6 +50,14 @@ int lush_ray_prep_fwd(const float* rays, float* ray_batch, int64_t R, int H, int
 int lush_ray_prep_bwd(const float* rays, const float* g_ray_batch, float* g_rays, int64_t R, int H,
                       int W, double focal, int ndc, void* stream);
 
+/* Rays of pixels [pix0, pix0 + n) (row-major pixel index) of ONE camera pose, generated and prepared in one pass:
+ * get_rays (reference utils/run_lushnerf_helpers.py:517-528) fused with the ray preparation above, replacing the
+ * per-frame [H, W, 3, 2] ray image of render_path (models/lushnerf.py:881-882).  c2w: device pointer to the
+ * [3, 4] (or [4, 4]) camera-to-world matrix, row stride c2w_stride floats.  Pixel centres at +0.5 like this
+ * package's get_rays; the NDC constants use fx as the reference does (K[0][0]). */
+int lush_ray_gen_prep(const float* c2w, int c2w_stride, int H, int W, double fx, double fy, double cx, double cy,
+                      float near, float far, int ndc, int64_t pix0, int64_t n, float* ray_batch, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Coarse sample placement.  Replaces models/lushnerf.py:389-412 (render_rays) / :501-523:
  *   t = linspace(0,1,S) (passed in as t_vals[S], computed by the host exactly as the reference

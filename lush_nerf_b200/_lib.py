@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblushnerf_b200.so")
+LIB_PATH = os.environ.get("LUSH_LIB_PATH") or os.path.join(_HERE, "liblushnerf_b200.so")   # override: A/B runs of two builds
 
 
 class MlpDesc(Structure):
@@ -49,6 +49,8 @@ _SIGNATURES = {
     "lush_launch_count": (c_int64, []),
     "lush_ray_prep_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, c_double, c_float, c_float, c_int, _P]),
     "lush_ray_prep_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_double, c_int, _P]),
+    "lush_ray_gen_prep": (c_int, [_P, c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_float, c_float,
+                                  c_int, c_int64, c_int64, _P, _P]),
     "lush_stratified_z": (c_int, [_P, c_int, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "lush_composite_fwd": (c_int, [_P, _P, _P, c_int, _P, c_float, c_int, _P, _P, _P, _P, _P, _P, c_int64,
                                    c_int, _P]),

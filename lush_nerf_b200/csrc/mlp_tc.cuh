@@ -168,9 +168,10 @@ __host__ __device__ constexpr uint32_t stash_off(uint32_t ncg, uint32_t r, uint3
 // 32 columns (4 groups of 8) of one row of a [128 x 8*ncg] stash blob; c = first column
 __device__ __forceinline__ void store_chunk_global(uint8_t* blob, int ncg, int c, int row, const uint32_t (&pw)[16]) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
-    *reinterpret_cast<uint4*>(blob + stash_off(ncg, row, (c >> 3) + g)) =
-        make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
+  for (int g = 0; g < 4; ++g)   // written once, read once by a later kernel: streaming stores (evict-first in L2)
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(blob + stash_off(ncg, row, (c >> 3) + g)),
+                 "r"(pw[4 * g]), "r"(pw[4 * g + 1]), "r"(pw[4 * g + 2]), "r"(pw[4 * g + 3])
+                 : "memory");
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -13,12 +13,8 @@ struct NdcConst {
 // ------------------------------------------------------------------------------------------------
 // ray_prep  (reference models/lushnerf.py:706-729 + helpers:542-562)
 // ------------------------------------------------------------------------------------------------
-__global__ void ray_prep_fwd_kernel(const float* __restrict__ rays, float* __restrict__ out,
-                                    int64_t R, NdcConst k, float near, float far, int ndc) {
-  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= R) return;
-  const float* p = rays + r * 6;
-  float ox = p[0], dx = p[1], oy = p[2], dy = p[3], oz = p[4], dz = p[5];
+__device__ __forceinline__ void ray_prep_store(float ox, float oy, float oz, float dx, float dy, float dz, NdcConst k,
+                                               float near, float far, int ndc, float* __restrict__ q) {
   float n = sqrtf(dx * dx + dy * dy + dz * dz);
   float vx = dx / n, vy = dy / n, vz = dz / n;
   float o0 = ox, o1 = oy, o2 = oz, d0 = dx, d1 = dy, d2 = dz;
@@ -32,9 +28,42 @@ __global__ void ray_prep_fwd_kernel(const float* __restrict__ rays, float* __res
     d1 = k.cy * (dy / dz - py / pz);
     d2 = -2.f / pz;
   }
-  float* q = out + r * 11;
   q[0] = o0; q[1] = o1; q[2] = o2; q[3] = d0; q[4] = d1; q[5] = d2;
   q[6] = near; q[7] = far; q[8] = vx; q[9] = vy; q[10] = vz;
+}
+
+__global__ void ray_prep_fwd_kernel(const float* __restrict__ rays, float* __restrict__ out,
+                                    int64_t R, NdcConst k, float near, float far, int ndc) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float* p = rays + r * 6;
+  ray_prep_store(p[0], p[2], p[4], p[1], p[3], p[5], k, near, far, ndc, out + r * 11);
+}
+
+// Rays of pixels [pix0, pix0 + n) of one pose, generated on the fly and prepared in the same pass: get_rays
+// (reference helpers:517-528: dirs = ((i + .5 - cx)/fx, -(j + .5 - cy)/fy, -1), d = sum_k dirs_k c2w[:, k],
+// o = c2w[:, 3]) fused with the ray preparation above -- the [H, W, 3, 2] ray image of render_path
+// (models/lushnerf.py:881-882) is never materialised.
+struct PinholeConst {
+  float ax, ay, fx, fy;   // (.5 - cx), (.5 - cy) formed in double like the Python expression, then fp32
+};
+__global__ void ray_gen_prep_kernel(const float* __restrict__ c2w, int c2w_stride, PinholeConst cam, int W,
+                                    int64_t pix0, int64_t n, float* __restrict__ out, NdcConst k, float near,
+                                    float far, int ndc) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int64_t p = pix0 + t;
+  const int64_t j = p / W;
+  const float fi = (float)(p - j * W), fj = (float)j;
+  const float u = (fi + cam.ax) / cam.fx, v = -((fj + cam.ay) / cam.fy), w = -1.f;
+  float d[3], o[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float* row = c2w + r * c2w_stride;
+    d[r] = (u * row[0] + v * row[1]) + w * row[2];
+    o[r] = row[3];
+  }
+  ray_prep_store(o[0], o[1], o[2], d[0], d[1], d[2], k, near, far, ndc, out + t * 11);
 }
 
 __global__ void ray_prep_bwd_kernel(const float* __restrict__ rays, const float* __restrict__ g,
@@ -340,6 +369,22 @@ extern "C" int lush_ray_prep_fwd(const float* rays, float* ray_batch, int64_t R,
   ray_prep_fwd_kernel<<<(unsigned)ceil_div(R, th), th, 0, (cudaStream_t)stream>>>(
       rays, ray_batch, R, make_ndc(H, W, focal), near, far, ndc);
   LUSH_LAUNCH_CHECK("ray_prep_fwd");
+  return 0;
+}
+
+extern "C" int lush_ray_gen_prep(const float* c2w, int c2w_stride, int H, int W, double fx, double fy, double cx,
+                                 double cy, float near, float far, int ndc, int64_t pix0, int64_t n,
+                                 float* ray_batch, void* stream) {
+  LUSH_REQUIRE(c2w && ray_batch && c2w_stride >= 4 && H > 0 && W > 0 && fx != 0.0 && fy != 0.0,
+               "ray_gen_prep: bad arguments");
+  LUSH_REQUIRE(pix0 >= 0 && n >= 0 && pix0 + n <= (int64_t)H * W, "ray_gen_prep: pixel range outside the image");
+  if (n == 0) return 0;
+  PinholeConst cam;
+  cam.ax = (float)(0.5 - cx); cam.ay = (float)(0.5 - cy); cam.fx = (float)fx; cam.fy = (float)fy;
+  int th = 256;
+  ray_gen_prep_kernel<<<(unsigned)ceil_div(n, th), th, 0, (cudaStream_t)stream>>>(
+      c2w, c2w_stride, cam, W, pix0, n, ray_batch, make_ndc(H, W, fx), near, far, ndc);
+  LUSH_LAUNCH_CHECK("ray_gen_prep");
   return 0;
 }
 

@@ -398,7 +398,16 @@ class NeRFAll(nn.Module):
     def render_infer(self, H, W, K, chunk, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
                      c2w_staticcam=None, use_awp=False, allkernel=0, kernelpixel=None, render_noise=True, **kwargs):
         """[rgb, depth, acc, extras], noise_rgb_raw  (reference :679-763)."""
-        rb, lead = self._ray_batch(H, W, K, rays, ndc, near, far, use_viewdirs, c2w_staticcam)
+        if rays is None:
+            # extension of the reference signature: no ray image given -> the rays of the pose are generated and
+            # prepared on the fly by one kernel (the reference always passes the [H, W, 3, 2] image, :881-883)
+            if c2w is None:
+                raise ValueError("render_infer needs rays or c2w")
+            if c2w_staticcam is not None or not use_viewdirs:
+                self._ray_batch(H, W, K, None, ndc, near, far, use_viewdirs, c2w_staticcam)   # raises
+            rb, lead = ops.ray_gen_prep(c2w, H, W, K, near, far, ndc), (H, W)
+        else:
+            rb, lead = self._ray_batch(H, W, K, rays, ndc, near, far, use_viewdirs, c2w_staticcam)
         rets, noises = [], []
         for i in range(0, rb.shape[0], chunk):
             ret, ret_noise = self.render_rays(rb[i:i + chunk], **kwargs)
@@ -483,7 +492,9 @@ class NeRFAll(nn.Module):
             if verbose:
                 print(i, time.time() - t)
             t = time.time()
-            rays = torch.stack(get_rays(H, W, K, c2w), dim=-1)
+            # rays come from the pose inside the ray-preparation kernel (LUSH_RAYGEN=0: materialise the ray image
+            # with get_rays like the reference, :881-882)
+            rays = None if os.environ.get("LUSH_RAYGEN", "1") != "0" else torch.stack(get_rays(H, W, K, c2w), dim=-1)
             (rgb, depth, acc, extras), rgb_noise = self.render_infer(H, W, K, chunk=chunk, rays=rays,
                                                                     c2w=c2w[:3, :4], **render_kwargs)
             rgbs.append(rgb)

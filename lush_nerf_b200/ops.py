@@ -66,6 +66,22 @@ def ray_prep(rays: torch.Tensor, H: int, W: int, focal: float, near=0.0, far=1.0
     return _RayPrep.apply(rays.reshape(-1, 3, 2), H, W, focal, near, far, ndc)
 
 
+def ray_gen_prep(c2w: torch.Tensor, H: int, W: int, K, near=0.0, far=1.0, ndc=True, pix0: int = 0, n: int = None):
+    """ray_batch [n, 11] of pixels [pix0, pix0 + n) of the pose c2w ([3,4] or [4,4]): get_rays + ray_prep in one
+    launch, nothing of size [H, W, 3, 2] is materialised (no gradient: poses are constants of the path)."""
+    if not c2w.is_cuda:
+        raise RuntimeError("lush_nerf_b200.ray_gen_prep needs a CUDA pose; there is no CPU fallback")
+    c2w = _f32c(c2w.detach())
+    if c2w.dim() != 2 or c2w.shape[0] < 3 or c2w.shape[1] != 4:
+        raise ValueError(f"ray_gen_prep: c2w must be [3,4] or [4,4], got {tuple(c2w.shape)}")
+    n = H * W - pix0 if n is None else n
+    out = _empty((n, 11), c2w)
+    check(lib().lush_ray_gen_prep(ptr(c2w, "c2w"), 4, int(H), int(W), float(K[0][0]), float(K[1][1]), float(K[0][2]),
+                                  float(K[1][2]), float(near), float(far), int(bool(ndc)), int(pix0), int(n), ptr(out),
+                                  stream()), "lush_ray_gen_prep")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # coarse sample placement (reference models/lushnerf.py:389-412)
 # ------------------------------------------------------------------------------------------------

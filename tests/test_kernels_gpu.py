@@ -237,6 +237,29 @@ def test_ray_prep_fwd_bwd(golden):
     close(out, O.ray_prep(rays, int(H), int(W), f, 2.0, 6.0, False), 1e-6, "no ndc")
 
 
+@pytest.mark.parametrize("ndc", [True, False])
+def test_ray_gen_prep_vs_oracle_get_rays(ndc):
+    """Rays generated from the pose inside the preparation kernel vs the oracle's get_rays (helpers:517-528) +
+    ray_prep; whole image, a pixel sub-range, a [4,4] pose.  2e-6: the NDC divisions amplify the last-bit
+    differences of the three-term direction sum."""
+    from lush_nerf_b200.synthetic import synthetic_poses
+    H, W, f = 40, 60, 50.0
+    K = np.array([[f, 0, 0.5 * W], [0, 1.1 * f, 0.45 * H], [0, 0, 1]])
+    c2w = torch.from_numpy(synthetic_poses(3, seed=1)[2]).float()
+    ro, rd = O.get_rays(H, W, K, c2w)
+    near, far = (0.0, 1.0) if ndc else (2.0, 6.0)
+    ref = O.ray_prep(torch.stack([ro, rd], -1).reshape(-1, 3, 2), H, W, f, near, far, ndc)
+    out = ops.ray_gen_prep(c2w.to(DEV), H, W, K, near, far, ndc)
+    close(out, ref, 2e-6, "ray_batch from pose")
+    sub = ops.ray_gen_prep(c2w.to(DEV), H, W, K, near, far, ndc, pix0=777, n=1000)
+    assert torch.equal(sub, out[777:1777])
+    c44 = torch.eye(4)
+    c44[:3] = c2w
+    assert torch.equal(ops.ray_gen_prep(c44.to(DEV), H, W, K, near, far, ndc), out)
+    with pytest.raises(RuntimeError):
+        ops.ray_gen_prep(c2w.to(DEV), H, W, K, near, far, ndc, pix0=H * W - 5, n=6)
+
+
 @pytest.mark.parametrize("perturb", [False, True])
 @pytest.mark.parametrize("lindisp", [False, True])
 def test_stratified_z(perturb, lindisp):

@@ -171,3 +171,24 @@ def test_numerical_guard_prints(det_state, capsys, monkeypatch):
         rb[:, 5] = -1; rb[:, 7] = 1; rb[:, 10] = -1
         m.render_rays(rb, 24, perturb=0.0, N_importance=16)
     assert "! [Numerical Error] rgb_map contains nan." in capsys.readouterr().out
+
+
+def test_stage3_consistency_path_vs_reference_golden(det_state):
+    """NeRFAll.forward(consist_loss=True) -> Render_Aligned_Pixel (reference models/lushnerf.py:664-668, :949-988):
+    same Python / numpy seeds (anchor view, 32 sampled match entries), the match table rebuilt from the generator's
+    formula, deterministic render kwargs.  Golden from the unmodified reference: tests/golden/make_golden_stage3.py."""
+    import random
+    from tests.golden import stage3_inputs as G3
+    data = np.load(G3.GOLDEN)
+    m = build(det_state).train()
+    K = np.array([[G3.FOCAL, 0, 0.5 * G3.W], [0, G3.FOCAL, 0.5 * G3.H], [0, 0, 1]])
+    am, mk = G3.stage3_tables()
+    random.seed(int(data["seed"]))
+    np.random.seed(int(data["seed"]))
+    rgb_align, certain = m(G3.H, G3.W, K, chunk=1024, poses=G3.stage3_poses().to(DEV), rays_info=None,
+                           consist_loss=True, Align_matrix=am.to(DEV), Align_mask=mk.to(DEV),
+                           render_kwargs=dict(G3.KW))
+    assert tuple(rgb_align.shape) == (G3.V, 32, 3) and tuple(certain.shape) == (G3.V, 32)
+    assert torch.equal(certain.cpu(), torch.from_numpy(data["certain"]))
+    close(rgb_align, torch.from_numpy(data["rgb_align"]), 3e-5, "rgb_align")
+    assert rgb_align.requires_grad          # the consistency loss trains the scene networks through these colours

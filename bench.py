@@ -263,8 +263,8 @@ def main():
 
     # ---- timed region 1b: the same step captured in ONE CUDA graph (Trainer.enable_cuda_graph) -- the product path
     graphed = False
-    # N > 1 runs eagerly: capturing the step together with its NCCL all-reduce hung on 2 x B200 (round 1)
-    if not args.no_graph and world == 1:
+    # N > 1: two graphs around an eager NCCL all-reduce (capturing the collective itself hung on 2 x B200 in round 1)
+    if not args.no_graph:
         try:
             graphed = bool(trainer.enable_cuda_graph(resident[0]))
             for i in range(args.warmup):
@@ -272,7 +272,13 @@ def main():
         except Exception as e:   # report, never hide: the eager path is the same kernels, only launched one by one
             print(f"[bench] CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}", file=sys.stderr)
             graphed = False
-            trainer._graph = None
+            trainer._graph = trainer._graph_tail = None
+    if world > 1:   # all ranks take the same path (a rank that failed to capture would still match collectives, but
+        ok = torch.tensor([1 if graphed else 0], device=dev)        # the line should describe ONE configuration)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if graphed and not bool(ok.item()):
+            graphed = False
+            trainer._graph = trainer._graph_tail = None
     ms_total = timed_pass(False) if graphed else ms_eager
     clocks = sampler.stop() if rank == 0 else None
 
@@ -287,8 +293,16 @@ def main():
     e2e_s = time.perf_counter() - t0
 
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    replicas_in_sync = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # identical Adam on identical all-reduced gradients: the replicas must still hold the same parameters
+        flat = torch.cat([p.detach().reshape(-1).double() for p in model.parameters()])
+        chk = torch.stack([flat.sum(), (flat * flat).sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replicas_in_sync = bool(torch.equal(lo, hi))
     ms_total, e2e_ms = t.tolist()
     rays_total = N_RAND * K_RAYS * world * args.steps
     value = rays_total / (ms_total * 1e-3)
@@ -359,7 +373,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "cuda_graph": graphed, "ms_per_step_eager": ms_eager / args.steps,
+            "cuda_graph": graphed, "ms_per_step_eager": ms_eager / args.steps, "replicas_in_sync": replicas_in_sync,
             "pixels_per_s": value / K_RAYS,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tflops"]) if achieved else None,

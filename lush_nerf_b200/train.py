@@ -31,7 +31,9 @@ def shard_rows(n: int, rank: int, world: int):
 
 
 class FlatGradAllReduce:
-    """Packs the gradients of `params` into one flat fp32 buffer, all-reduces it once, unpacks."""
+    """Packs the gradients of `params` into one flat fp32 buffer, all-reduces it once, unpacks.
+    The three phases are separate methods so that a captured training step can keep the NCCL call outside its
+    CUDA graphs (pack at the end of graph A, all-reduce eagerly, unpack at the start of graph B)."""
 
     def __init__(self, params, group=None):
         self.params = [p for p in params if p.requires_grad]
@@ -39,15 +41,25 @@ class FlatGradAllReduce:
         self.numel = sum(p.numel() for p in self.params)
         self.flat = None
 
-    def __call__(self):
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+    def active(self):
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def pack(self):
+        if not self.active():
             return
         # parameters without a gradient (NeRF_Noise.alpha_linear) contribute zeros and receive nothing back
-        with_grad = [p for p in self.params if p.grad is not None]
         pieces = [p.grad.reshape(-1) if p.grad is not None else p.new_zeros(p.numel()) for p in self.params]
         self.flat = torch.cat(pieces)                     # one multi-tensor pack kernel instead of one copy per tensor
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+
+    def reduce(self):
+        if self.active():
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+
+    def unpack(self):
+        if not self.active():
+            return
         self.flat.div_(dist.get_world_size(self.group))
+        with_grad = [p for p in self.params if p.grad is not None]
         views, off = [], 0
         for p in self.params:
             n = p.numel()
@@ -55,6 +67,11 @@ class FlatGradAllReduce:
                 views.append(self.flat[off:off + n].view_as(p.grad))
             off += n
         torch._foreach_copy_([p.grad for p in with_grad], views)   # one multi-tensor unpack kernel
+
+    def __call__(self):
+        self.pack()
+        self.reduce()
+        self.unpack()
 
 
 class Trainer:
@@ -80,9 +97,9 @@ class Trainer:
         self.allreduce = FlatGradAllReduce(params, group)
         self.render_kwargs = render_kwargs or {}
         self.lrate, self.global_step = lrate, 0
-        self._graph, self._static, self._static_loss = None, None, None
+        self._graph, self._graph_tail, self._static, self._static_loss = None, None, None, None
 
-    def _step_body(self, batch, force_naive=False, allkernel=True, chunk=1024 * 32):
+    def _fwd_bwd(self, batch, force_naive=False, allkernel=True, chunk=1024 * 32):
         m = self.model
         out = m(self.H, self.W, self.K, chunk=chunk, rays=batch["rays"],
                 rays_info={"images_idx": batch["images_idx"]}, retraw=True, force_naive=force_naive,
@@ -90,8 +107,17 @@ class Trainer:
         loss = ops.blur_loss(out[0], out[1], batch["rgbsf"])      # value + gradient, one launch
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
-        self.allreduce()
+        self.allreduce.pack()
+        return loss
+
+    def _finish(self):
+        self.allreduce.unpack()
         self.optimizer.step()
+
+    def _step_body(self, batch, force_naive=False, allkernel=True, chunk=1024 * 32):
+        loss = self._fwd_bwd(batch, force_naive, allkernel, chunk)
+        self.allreduce.reduce()
+        self._finish()
         return loss
 
     def step(self, batch, force_naive=False, allkernel=True, chunk=1024 * 32):
@@ -101,6 +127,9 @@ class Trainer:
             for k, v in self._static.items():       # H2D (or D2D) into the captured input buffers
                 v.copy_(batch[k], non_blocking=True)
             self._graph.replay()
+            if self._graph_tail is not None:        # multi-GPU: the NCCL all-reduce runs between the two graphs
+                self.allreduce.reduce()
+                self._graph_tail.replay()
             self.global_step += 1
             return self._static_loss
         loss = self._step_body(batch, force_naive, allkernel, chunk)
@@ -108,14 +137,14 @@ class Trainer:
         return loss
 
     def enable_cuda_graph(self, sample_batch, warmup=3):
-        """Capture one whole training step (forward, loss, backward, gradient all-reduce, Adam) in a CUDA graph:
-        ~240 launches become one graph launch.  The batch is copied into static buffers before every replay;
-        random draws (stratified jitter, sigma noise) come from the graph-registered default CUDA generator.
-        The NaN/Inf guard of the model runs in deferred mode (flag word inspected by `check_numerics()`)."""
+        """Capture one whole training step in CUDA graphs: ~72 kernel launches become one graph launch.
+        World size 1: ONE graph (forward, loss, backward, Adam).  World size > 1: TWO graphs around an eager NCCL
+        all-reduce of the flat gradient (A: forward, loss, backward, pack; B: unpack, Adam) -- capturing the
+        collective itself hung on 2 x B200 in round 1, and NCCL's launch is one call either way.
+        The batch is copied into static buffers before every replay; random draws (stratified jitter, sigma noise)
+        come from the graph-registered default CUDA generator.  The NaN/Inf guard of the model runs in deferred
+        mode (flag word inspected by `check_numerics()`)."""
         import os
-        if dist.is_initialized() and dist.get_world_size(self.allreduce.group) > 1:
-            # capturing the NCCL all-reduce together with the step hung on 2 x B200 (round 1, unresolved)
-            raise RuntimeError("Trainer.enable_cuda_graph supports world size 1 only")
         if self._graph is not None:
             return True
         if not hasattr(self.optimizer, "_sync_lr"):
@@ -127,14 +156,23 @@ class Trainer:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(warmup):                 # every rank runs the same number of (collective) warm-up steps
                 self._step_body(self._static)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        split = self.allreduce.active()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._static_loss = self._step_body(self._static)
-        self._graph = g
+            if split:
+                self._static_loss = self._fwd_bwd(self._static)
+            else:
+                self._static_loss = self._step_body(self._static)
+        tail = None
+        if split:
+            tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(tail, pool=g.pool()):   # same memory pool: reads graph A's gradients and flat buffer
+                self._finish()
+        self._graph, self._graph_tail = g, tail
         self.global_step += warmup
         return True
 

@@ -46,7 +46,7 @@ __device__ __forceinline__ void small_dense(int t, int N, const float* __restric
       if (x == nullptr) continue;
       // every thread streams its own weight row: 16-byte loads when the row segment is aligned (4x fewer L1 requests)
       const bool vec = ((fan | wc) & 3) == 0 && (K & 3) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0;
-#pragma unroll 2
+#pragma unroll 8                             // 8 weight loads in flight: the row walk is bound by L2 latency, not by FMAs
       for (int kq = 0; kq < K; kq += 4) {     // shared rows are zero-padded to a multiple of 4
         float w[4];
         if (vec) {
@@ -192,7 +192,7 @@ __device__ __forceinline__ void small_dgrad(int t, int N, int K, const float (*d
     float acc[TM];
 #pragma unroll
     for (int r = 0; r < TM; ++r) acc[r] = 0.f;
-#pragma unroll 2
+#pragma unroll 8
     for (int n = 0; n < N; ++n) {
       const float w = __ldg(Wt + (int64_t)n * fan + wc + t);
 #pragma unroll

@@ -5,9 +5,9 @@
 // Everything up to (r, v, ccw) depends on the image index alone, so the network runs once per IMAGE (rows of
 // the embedding table) and every ray gathers the row of its image; the backward sums the per-ray gradients per
 // image first.  A CTA owns MOTION_ROWS images and keeps every activation of those rows in shared memory through
-// the whole network; a warp owns an output unit, its lanes stride the (contiguous) fan-in of that unit, so the
-// weights are read coalesced straight from L2 and never staged.  ~25 k parameters: the kernels are latency
-// bound by design -- they replace ~90 library launches of a few microseconds each.
+// the whole network, next to a copy of all weights and biases (~100 KB, staged once per CTA with every load in
+// flight); a warp owns an output unit, its lanes stride the (contiguous) fan-in of that unit.  ~25 k parameters:
+// the kernels are latency bound by design -- they replace ~90 library launches of a few microseconds each.
 #include "common.cuh"
 
 namespace lush {
@@ -16,7 +16,22 @@ constexpr int MOTION_ROWS = 8;
 constexpr int MOTION_THREADS = 512;
 constexpr int MOTION_CHUNK = 4096;       // rays whose image slot is staged in shared memory at a time
 
-__device__ __forceinline__ int motion_src(const lush_dense_layer& L, int k) {
+// The layer table sits in kernel-parameter (constant) space and is indexed with a runtime layer number: every field
+// access is an indexed constant load with ~50 cycles of latency.  Each layer's scalars are therefore read ONCE into
+// registers (LayerRegs) before its loops.
+struct LayerRegs {
+  const float* w; const float* b; float* gw; float* gb;
+  int in0_off, in0_dim, in1_off, in1_dim, out_off, out_dim, act;
+};
+__device__ __forceinline__ LayerRegs motion_layer(const lush_motion_net& net, int l) {
+  const lush_dense_layer& L = net.layers[l];
+  LayerRegs r;
+  r.w = L.w; r.b = L.b; r.gw = L.gw; r.gb = L.gb;
+  r.in0_off = L.in0_off; r.in0_dim = L.in0_dim; r.in1_off = L.in1_off; r.in1_dim = L.in1_dim;
+  r.out_off = L.out_off; r.out_dim = L.out_dim; r.act = L.act;
+  return r;
+}
+__device__ __forceinline__ int motion_src(const LayerRegs& L, int k) {
   return k < L.in0_dim ? L.in0_off + k : L.in1_off + (k - L.in0_dim);
 }
 
@@ -43,41 +58,62 @@ __device__ __forceinline__ float motion_reduce_rows(float (&acc)[MOTION_ROWS], i
   return v;
 }
 
-// Pull every weight matrix (~100 KB in all) towards L1 at kernel start: the layer loop then waits on L1 hits
-// instead of one L2 round trip per output unit.
-__device__ __forceinline__ void motion_prefetch_weights(const lush_motion_net& net, int tid) {
+// All weight matrices (~100 KB) are copied into shared memory once per CTA (coalesced, every load in flight at the
+// same time): the layer loops then read them with shared-memory latency instead of one L2 round trip per output unit.
+// `stage_w` = 0 (network too large for shared memory): read them from global memory in place.
+__device__ __forceinline__ void motion_stage_weights(const lush_motion_net& net, float* s_w, int tid) {
+  int base = 0;
   for (int l = 0; l < net.n_layers; ++l) {
     const lush_dense_layer& L = net.layers[l];
     const int total = L.out_dim * (L.in0_dim + L.in1_dim);
-    for (int i = tid * 32; i < total; i += MOTION_THREADS * 32)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(L.w + i));
+#pragma unroll 8
+    for (int i = tid; i < total; i += MOTION_THREADS) s_w[base + i] = L.w[i];
+    base += total;
   }
+  for (int l = 0; l < net.n_layers; ++l) {               // biases behind the weights
+    const lush_dense_layer& L = net.layers[l];
+    for (int i = tid; i < L.out_dim; i += MOTION_THREADS) s_w[base + i] = L.b[i];
+    base += L.out_dim;
+  }
+}
+__device__ __forceinline__ int motion_bias_offset(const lush_motion_net& net, int l) {
+  int base = 0;
+  for (int i = 0; i < net.n_layers; ++i) base += net.layers[i].out_dim * (net.layers[i].in0_dim + net.layers[i].in1_dim);
+  for (int i = 0; i < l; ++i) base += net.layers[i].out_dim;
+  return base;
+}
+__device__ __forceinline__ int motion_weight_offset(const lush_motion_net& net, int l) {
+  int base = 0;
+  for (int i = 0; i < l; ++i) base += net.layers[i].out_dim * (net.layers[i].in0_dim + net.layers[i].in1_dim);
+  return base;
 }
 
 __global__ void __launch_bounds__(MOTION_THREADS)
 motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __restrict__ embed, int n_img,
                   const int64_t* __restrict__ idx, int64_t N, float* __restrict__ rows,
-                  float* __restrict__ out_r, float* __restrict__ out_v, float* __restrict__ out_ccw) {
+                  float* __restrict__ out_r, float* __restrict__ out_v, float* __restrict__ out_ccw, int stage_w) {
   extern __shared__ float s_act[];                      // [MOTION_ROWS][rw]
   __shared__ int s_slot[MOTION_CHUNK];
   const int rw = net.row_width, C = net.embed_dim, M = net.num_motion;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MOTION_THREADS / 32;
   const int row0 = blockIdx.x * MOTION_ROWS;
   const int nrows = min(MOTION_ROWS, n_img - row0);
-  motion_prefetch_weights(net, tid);
+  float* s_w = s_act + MOTION_ROWS * rw;                // staged weights (stage_w)
+  if (stage_w) motion_stage_weights(net, s_w, tid);
   for (int t = tid; t < MOTION_ROWS * C; t += MOTION_THREADS) {
     int r = t / C, k = t - r * C;
     s_act[r * rw + k] = r < nrows ? embed[(int64_t)(row0 + r) * C + k] : 0.f;
   }
   __syncthreads();
+  int woff = 0, boff = motion_bias_offset(net, 0);       // running offsets into the staged weights / biases
   for (int l = 0; l < net.n_layers; ++l) {
-    const lush_dense_layer& L = net.layers[l];
+    const LayerRegs L = motion_layer(net, l);
     const int in_dim = L.in0_dim + L.in1_dim;
     for (int o = warp; o < L.out_dim; o += nwarps) {
       float acc[MOTION_ROWS];
 #pragma unroll
       for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = 0.f;
-      const float* wrow = L.w + (int64_t)o * in_dim;
+      const float* wrow = (stage_w ? s_w + woff : L.w) + (int64_t)o * in_dim;
 #pragma unroll 2
       for (int k = lane; k < in_dim; k += 32) {
         float w = wrow[k];
@@ -85,9 +121,11 @@ motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __re
 #pragma unroll
         for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = fmaf(w, a[r * rw], acc[r]);
       }
-      const float mine = motion_reduce_rows(acc, lane) + L.b[o];       // lane holds row motion_row_of(lane)
+      const float mine = motion_reduce_rows(acc, lane) + (stage_w ? s_w[boff + o] : L.b[o]);       // lane holds row motion_row_of(lane)
       if ((lane & 3) == 0) s_act[motion_row_of(lane) * rw + L.out_off + o] = L.act ? fmaxf(mine, 0.f) : mine;
     }
+    woff += L.out_dim * in_dim;
+    boff += L.out_dim;
     __syncthreads();
   }
   // stash the rows (pre-head values) for the backward
@@ -121,15 +159,20 @@ motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __re
       s_slot[i] = (r >= 0 && r < nrows) ? (int)r : -1;
     }
     __syncthreads();
-    for (int i = tid; i < cn; i += MOTION_THREADS) {
+#pragma unroll 4
+    for (int t = tid; t < cn * nr; t += MOTION_THREADS) {   // consecutive threads -> consecutive output floats
+      const int i = t / nr, j = t - i * nr;
       const int r = s_slot[i];
-      if (r < 0) continue;
-      const float* a = s_act + r * rw;
-      float* pr = out_r + (n0 + i) * nr;
-      float* pv = out_v + (n0 + i) * nr;
-      float* pc = out_ccw + (n0 + i) * nc;
-      for (int j = 0; j < nr; ++j) { pr[j] = a[net.r_off + j]; pv[j] = a[net.v_off + j]; }
-      for (int j = 0; j < nc; ++j) pc[j] = a[net.w_off + j];
+      if (r >= 0) {
+        out_r[n0 * nr + t] = s_act[r * rw + net.r_off + j];
+        out_v[n0 * nr + t] = s_act[r * rw + net.v_off + j];
+      }
+    }
+#pragma unroll 4
+    for (int t = tid; t < cn * nc; t += MOTION_THREADS) {
+      const int i = t / nc, j = t - i * nc;
+      const int r = s_slot[i];
+      if (r >= 0) out_ccw[n0 * nc + t] = s_act[r * rw + net.w_off + j];
     }
   }
 }
@@ -138,7 +181,7 @@ __global__ void __launch_bounds__(MOTION_THREADS)
 motion_bwd_kernel(const __grid_constant__ lush_motion_net net, int n_img, const int64_t* __restrict__ idx,
                   int64_t N, const float* __restrict__ rows, const float* __restrict__ g_r,
                   const float* __restrict__ g_v, const float* __restrict__ g_ccw,
-                  float* __restrict__ g_embed) {
+                  float* __restrict__ g_embed, int stage_w) {
   extern __shared__ float s_mem[];
   __shared__ int s_slot[MOTION_CHUNK];
   const int rw = net.row_width, C = net.embed_dim, M = net.num_motion;
@@ -147,7 +190,8 @@ motion_bwd_kernel(const __grid_constant__ lush_motion_net net, int n_img, const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MOTION_THREADS / 32;
   const int row0 = blockIdx.x * MOTION_ROWS;
   const int nrows = min(MOTION_ROWS, n_img - row0);
-  motion_prefetch_weights(net, tid);
+  float* s_w = s_mem + 2 * MOTION_ROWS * rw;            // staged weights (stage_w)
+  if (stage_w) motion_stage_weights(net, s_w, tid);
   for (int t = tid; t < MOTION_ROWS * rw; t += MOTION_THREADS) {
     s_act[t] = t < nrows * rw ? rows[(int64_t)row0 * rw + t] : 0.f;
     s_g[t] = 0.f;
@@ -205,9 +249,11 @@ motion_bwd_kernel(const __grid_constant__ lush_motion_net net, int n_img, const 
     }
   }
   __syncthreads();
+  int woff = motion_weight_offset(net, net.n_layers);     // running offset into the staged weights (descending)
   for (int l = net.n_layers - 1; l >= 0; --l) {
-    const lush_dense_layer& L = net.layers[l];
+    const LayerRegs L = motion_layer(net, l);
     const int in_dim = L.in0_dim + L.in1_dim;
+    woff -= L.out_dim * in_dim;
     if (L.act) {
       for (int t = tid; t < MOTION_ROWS * L.out_dim; t += MOTION_THREADS) {
         int r = t / L.out_dim, o = t - r * L.out_dim;
@@ -235,6 +281,7 @@ motion_bwd_kernel(const __grid_constant__ lush_motion_net net, int n_img, const 
     }
     // input gradients: thread per input column, output units split over the thread groups
     if (l > 0 || g_embed) {
+      const float* wsrc = stage_w ? s_w + woff : L.w;
       const int groups = max(1, MOTION_THREADS / in_dim);
       for (int k = tid % in_dim, og = tid / in_dim; og < groups && k < in_dim; k += MOTION_THREADS) {
         float acc[MOTION_ROWS];
@@ -242,7 +289,7 @@ motion_bwd_kernel(const __grid_constant__ lush_motion_net net, int n_img, const 
         for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = 0.f;
 #pragma unroll 4
         for (int o = og; o < L.out_dim; o += groups) {
-          float w = L.w[(int64_t)o * in_dim + k];
+          float w = wsrc[(int64_t)o * in_dim + k];
           const float* g = s_g + L.out_off + o;
 #pragma unroll
           for (int r = 0; r < MOTION_ROWS; ++r) acc[r] = fmaf(w, g[r * rw], acc[r]);
@@ -259,6 +306,13 @@ motion_bwd_kernel(const __grid_constant__ lush_motion_net net, int n_img, const 
       int r = t / C, k = t - r * C;
       g_embed[(int64_t)(row0 + r) * C + k] = s_g[r * rw + k];
     }
+}
+
+static size_t motion_weight_bytes(const lush_motion_net* net) {
+  size_t n = 0;
+  for (int l = 0; l < net->n_layers; ++l)
+    n += (size_t)net->layers[l].out_dim * (net->layers[l].in0_dim + net->layers[l].in1_dim + 1);   // + bias
+  return n * sizeof(float);
 }
 
 static int motion_check(const lush_motion_net* net, const char* who) {
@@ -293,6 +347,9 @@ extern "C" int lush_rbk_motion_fwd(const lush_motion_net* net, const float* embe
   LUSH_REQUIRE(embed && n_img >= 1 && N >= 0 && rows && (N == 0 || (images_idx && r && v && ccw)),
                "rbk_motion_fwd: bad arguments");
   size_t smem = (size_t)MOTION_ROWS * net->row_width * sizeof(float);
+  const size_t wbytes = motion_weight_bytes(net);
+  const int stage_w = (smem + wbytes <= 180 * 1024) ? 1 : 0;
+  if (stage_w) smem += wbytes;
   LUSH_REQUIRE(smem <= 200 * 1024, "rbk_motion_fwd: activation row of %d floats does not fit shared memory",
                net->row_width);
   static bool attr_set = false;
@@ -303,7 +360,7 @@ extern "C" int lush_rbk_motion_fwd(const lush_motion_net* net, const float* embe
   }
   unsigned blocks = (unsigned)ceil_div(n_img, MOTION_ROWS);
   motion_fwd_kernel<<<blocks, MOTION_THREADS, smem, (cudaStream_t)stream>>>(*net, embed, n_img, images_idx, N, rows,
-                                                                            r, v, ccw);
+                                                                            r, v, ccw, stage_w);
   LUSH_LAUNCH_CHECK("rbk_motion_fwd");
   return 0;
 }
@@ -317,6 +374,9 @@ extern "C" int lush_rbk_motion_bwd(const lush_motion_net* net, int n_img, const 
   for (int l = 0; l < net->n_layers; ++l)
     LUSH_REQUIRE(net->layers[l].gw && net->layers[l].gb, "rbk_motion_bwd: layer %d has no gradient buffers", l);
   size_t smem = (size_t)2 * MOTION_ROWS * net->row_width * sizeof(float);
+  const size_t wbytes = motion_weight_bytes(net);
+  const int stage_w = (smem + wbytes <= 180 * 1024) ? 1 : 0;
+  if (stage_w) smem += wbytes;
   LUSH_REQUIRE(smem <= 200 * 1024, "rbk_motion_bwd: activation row of %d floats does not fit shared memory",
                net->row_width);
   static bool attr_set = false;
@@ -327,7 +387,7 @@ extern "C" int lush_rbk_motion_bwd(const lush_motion_net* net, int n_img, const 
   }
   unsigned blocks = (unsigned)ceil_div(n_img, MOTION_ROWS);
   motion_bwd_kernel<<<blocks, MOTION_THREADS, smem, (cudaStream_t)stream>>>(*net, n_img, images_idx, N, rows, g_r,
-                                                                            g_v, g_ccw, g_embed);
+                                                                            g_v, g_ccw, g_embed, stage_w);
   LUSH_LAUNCH_CHECK("rbk_motion_bwd");
   return 0;
 }

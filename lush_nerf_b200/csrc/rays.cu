@@ -375,7 +375,7 @@ extern "C" int lush_ray_prep_fwd(const float* rays, float* ray_batch, int64_t R,
 extern "C" int lush_ray_gen_prep(const float* c2w, int c2w_stride, int H, int W, double fx, double fy, double cx,
                                  double cy, float near, float far, int ndc, int64_t pix0, int64_t n,
                                  float* ray_batch, void* stream) {
-  LUSH_REQUIRE(c2w && ray_batch && c2w_stride >= 4 && H > 0 && W > 0 && fx != 0.0 && fy != 0.0,
+  LUSH_REQUIRE(c2w && (ray_batch || n == 0) && c2w_stride >= 4 && H > 0 && W > 0 && fx != 0.0 && fy != 0.0,
                "ray_gen_prep: bad arguments");
   LUSH_REQUIRE(pix0 >= 0 && n >= 0 && pix0 + n <= (int64_t)H * W, "ray_gen_prep: pixel range outside the image");
   if (n == 0) return 0;

@@ -348,6 +348,33 @@ def test_rbk_motion_fused_matches_torch_layers(cfg):
         assert rel_l2(gf[n], gt[n]) < 2e-5, (n, rel_l2(gf[n], gt[n]))
 
 
+def test_new_entry_points_edge_cases():
+    """Empty / degenerate inputs of the round's new entry points: no rays for the motion network, a pixel range of
+    length 0, an optimiser step with no gradients, mismatched loss shapes, CPU tensors (no fallback)."""
+    from lush_nerf_b200.models.lushnerf import RBK
+    from lush_nerf_b200.optim import Adam
+    rbk = RBK(num_img=5, view_embed_ch=16, D_rbk=2, W_rbk=32, skips_rbk=[4], num_motion_rbk=2, D_rbk_r=1, W_rbk_r=16,
+              output_ch_rbk_r=3, D_rbk_v=1, W_rbk_v=16, output_ch_rbk_v=3, D_rbk_w=1, W_rbk_w=16, rbk_se_rv_window=0.1,
+              use_dpnerf=True, rbk_use_origin=True, near=0.0, far=1.0, ndc=True).RBK.to(DEV)
+    r, v, w = rbk.motion_params({"images_idx": torch.zeros(0, 1, dtype=torch.long, device=DEV)})
+    assert r.shape == (0, 6) and v.shape == (0, 6) and w.shape == (0, 3)
+    r, v, w = rbk.motion_params({"images_idx": torch.full((7, 1), 4, dtype=torch.long, device=DEV)})
+    assert torch.isfinite(r).all() and torch.allclose(w.sum(-1), torch.ones(7, device=DEV), atol=1e-6)
+    assert torch.equal(r[0], r[6])                                   # same image -> same motion
+    K = np.array([[50.0, 0, 30.0], [0, 50.0, 20.0], [0, 0, 1]])
+    assert ops.ray_gen_prep(torch.eye(4, device=DEV), 40, 60, K, n=0).shape == (0, 11)
+    p = torch.nn.Parameter(torch.ones(3, device=DEV))
+    opt = Adam([p], lr=0.1)
+    opt.step()                                                       # no gradient anywhere: a no-op
+    assert torch.equal(p.detach().cpu(), torch.ones(3)) and len(opt.state_dict()["state"]) == 0
+    with pytest.raises(RuntimeError):
+        Adam([torch.nn.Parameter(torch.ones(3))], lr=0.1)            # CPU parameter: no fallback
+    with pytest.raises(RuntimeError):
+        ops.blur_loss(torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(4, 3))
+    with pytest.raises(RuntimeError):
+        ops.ray_gen_prep(torch.eye(4), 40, 60, K)
+
+
 def test_blend_tonemap_fwd_bwd():
     N, K = 33, 5
     g = torch.Generator().manual_seed(0)

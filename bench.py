@@ -285,12 +285,28 @@ def main():
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step
     barrier()
     t0 = time.perf_counter()
+    # Every step: H2D of the step's batch from pinned memory (straight into the captured step's static input buffers
+    # when the step is a graph) and a D2H read of its loss.  The read is pipelined like a training loop's logging: the
+    # loss of step i is copied into pinned memory asynchronously and consumed while step i+1 is already queued; the
+    # last one is read synchronously inside the timed region.
+    loss_pin = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    losses_host = []
     for i in range(args.steps):
-        b = {k: v.to(dev, non_blocking=True) for k, v in host[args.warmup + i].items()}
+        hb = host[args.warmup + i]
+        b = hb if graphed else {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
         loss = trainer.step(b)
-        loss_host = float(loss.item())
+        loss_pin[i & 1].copy_(loss.detach(), non_blocking=True)
+        loss_ev[i & 1].record()
+        if i > 0:
+            loss_ev[(i - 1) & 1].synchronize()
+            losses_host.append(float(loss_pin[(i - 1) & 1]))
+    loss_ev[(args.steps - 1) & 1].synchronize()
+    losses_host.append(float(loss_pin[(args.steps - 1) & 1]))
+    loss_host = losses_host[-1]
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert len(losses_host) == args.steps and all(np.isfinite(losses_host)), "e2e: a step's loss did not come back finite"
 
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     replicas_in_sync = None

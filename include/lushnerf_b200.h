@@ -264,6 +264,11 @@ int lush_tc_selftest(const void* a_blob, const void* b_blob, float* d_out, int N
  * tcgen05.mma M=128 K=16 from one thread; out_cycles[0] = issue cycles, out_cycles[1] = cycles to completion.
  * flags (per block of 8 MMAs): 1 = tcgen05.commit, 2 = tcgen05.fence::after_thread_sync, 4 = mbarrier wait. */
 int lush_tc_microbench(long long* out_cycles, int N, int nacc, int a_tmem, int iters, int flags, void* stream);
+/* Diagnostics: CTA-pair UMMA (cta_group::2).  D[256 x N] = A[256 x K] . B[N x K]^T on a cluster of two CTAs; a_blob =
+ * two consecutive K-major canonical [128 x K] blobs (rows 0..127, 128..255), b_blob = two consecutive K-major
+ * canonical [N/2 x K] blobs; d_out [256, N] fp32 row-major.  Pins the conventions a 2-CTA chain kernel needs. */
+int lush_tc_selftest_pair(const void* a_blob, const void* b_blob, float* d_out, int N, int K, void* stream);
+
 /* Diagnostics: every CTA streams the same nblocks x block_bytes image from L2 through a 3-stage shared-memory ring
  * `iters` times, unicast (cluster = 1) or with each CTA of a cluster fetching 1/cluster of a block and multicasting
  * it (cluster = 2, 4).  out_cycles[grid] = cycles per CTA.  Measures the weight-delivery rate of the chain kernels. */

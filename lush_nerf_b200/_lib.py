@@ -76,6 +76,7 @@ _SIGNATURES = {
     "lush_adam_step": (c_int, [POINTER(AdamSeg), c_int, _P, _P, _P, c_double, c_double, c_double, _P]),
     "lush_tc_selftest": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "lush_tc_microbench": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "lush_tc_selftest_pair": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "lush_tc_bcast_bench": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "lush_debug_read_chain_trace": (c_int, [_P, c_int]),
     "lush_debug_read_chain_trace_bwd": (c_int, [_P, c_int]),

@@ -293,3 +293,94 @@ extern "C" int lush_tc_bcast_bench(const void* src, int nblocks, int block_bytes
   LUSH_LAUNCH_CHECK("tc_bcast_bench");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair self-test (cta_group::2): D[256 x N] = A[256 x K] * B[N x K]^T with a cluster of two CTAs.  CTA r stages
+// rows [128 r, 128 r + 128) of A and rows [N/2 r, N/2 r + N/2) of B (both K-major canonical blobs) in ITS shared
+// memory; the leader issues one M=256 MMA per K=16 that reads both CTAs' operands, and each CTA finds its 128 rows of D
+// (all N columns) in its own tensor memory.  This is the mode that halves the weight bytes an SM has to stage and read
+// (shared-memory traffic); not on the product path.
+// ------------------------------------------------------------------------------------------------
+namespace lush {
+using namespace tc;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+tc_selftest_pair_kernel(const __half* __restrict__ a_blob, const __half* __restrict__ b_blob, float* __restrict__ d_out,
+                        int N, int K) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t a_bytes = 128u * K * 2u, b_bytes = (uint32_t)(N / 2) * K * 2u;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + a_bytes;
+  const uint8_t* ga = reinterpret_cast<const uint8_t*>(a_blob) + (size_t)rank * a_bytes;
+  const uint8_t* gb = reinterpret_cast<const uint8_t*>(b_blob) + (size_t)rank * b_bytes;
+  for (uint32_t i = tid * 16; i < a_bytes; i += 128 * 16) *reinterpret_cast<uint4*>(sa + i) = *reinterpret_cast<const uint4*>(ga + i);
+  for (uint32_t i = tid * 16; i < b_bytes; i += 128 * 16) *reinterpret_cast<uint4*>(sb + i) = *reinterpret_cast<const uint4*>(gb + i);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {   // the same warp id in both CTAs, the same shared-memory address for the result
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' operands and barriers are in place before the leader issues
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = make_idesc_f16(256, N, 0, 0);
+    const uint32_t a_lbo = 128u * 16u, b_lbo = (uint32_t)(N / 2) * 16u;
+    for (int k = 0; k < K / 16; ++k) {
+      const uint64_t ad = make_smem_desc(smem_u32(sa) + k * 2u * a_lbo, a_lbo, 128u);
+      const uint64_t bd = make_smem_desc(smem_u32(sb) + k * 2u * b_lbo, b_lbo, 128u);
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_base),
+          "l"(ad), "l"(bd), "r"(idesc), "r"(k > 0 ? 1u : 0u)
+          : "memory");
+    }
+    // completion is signalled on `bar` of BOTH CTAs (same shared-memory offset)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(&bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const int row = tid;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) d_out[(size_t)(128 * rank + row) * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // neither CTA frees tensor memory while its peer may still be reading
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+}  // namespace lush
+
+extern "C" int lush_tc_selftest_pair(const void* a_blob, const void* b_blob, float* d_out, int N, int K, void* stream) {
+  using namespace lush;
+  LUSH_REQUIRE(a_blob && b_blob && d_out && N >= 32 && N <= 256 && N % 32 == 0 && K >= 16 && K % 16 == 0,
+               "tc_selftest_pair: bad arguments");
+  const size_t smem = (size_t)128 * K * 2 + (size_t)(N / 2) * K * 2;
+  LUSH_REQUIRE(smem <= 200 * 1024, "tc_selftest_pair: operands do not fit shared memory");
+  LUSH_REQUIRE(cudaFuncSetAttribute(tc_selftest_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) ==
+                   cudaSuccess,
+               "tc_selftest_pair: cannot raise the shared memory limit");
+  tc_selftest_pair_kernel<<<2, 128, smem, (cudaStream_t)stream>>>((const __half*)a_blob, (const __half*)b_blob, d_out, N, K);
+  LUSH_LAUNCH_CHECK("tc_selftest_pair");
+  return 0;
+}

@@ -35,6 +35,11 @@ class Adam(torch.optim.Optimizer):
         self._counter = torch.zeros(1, dtype=torch.int32, device=self._dev)
         self._table, self._table_key = None, None
 
+    def add_param_group(self, param_group):
+        if hasattr(self, "_steps"):      # the device-side step / learning-rate tables are sized at construction
+            raise NotImplementedError("lush_nerf_b200.optim.Adam: add_param_group after construction is not supported")
+        super().add_param_group(param_group)
+
     def _sync_lr(self):
         """Push edited learning rates to the device (a small copy on the current stream, outside any graph)."""
         cur = [float(g["lr"]) for g in self.param_groups]

@@ -55,3 +55,22 @@ def test_umma_a_operand_from_tensor_memory(b_mode, N, K):
     out = run(A, B, 2, b_mode)
     err = (out - ref).abs().max().item()
     assert err < 2e-3, f"TS-mode UMMA wrong: max err {err:.3e}"
+
+
+@pytest.mark.parametrize("N,K", [(256, 64), (128, 32), (256, 256), (64, 16)])
+def test_umma_cta_pair(N, K):
+    """cta_group::2: one M=256 MMA per K=16 on a cluster of two CTAs; CTA r stages rows [128r, 128r+128) of A and rows
+    [N/2 r, N/2 r + N/2) of B in its own shared memory and finds its 128 rows of D in its own tensor memory."""
+    g = torch.Generator().manual_seed(N * 13 + K)
+    A = (torch.randn(256, K, generator=g) * 0.5).half()
+    B = (torch.randn(N, K, generator=g) * 0.5).half()
+    ref = A.float() @ B.float().t()
+    a_blob = torch.cat([to_blob(A[:128].contiguous()), to_blob(A[128:].contiguous())]).cuda()
+    b_blob = torch.cat([to_blob(B[:N // 2].contiguous()), to_blob(B[N // 2:].contiguous())]).cuda()
+    out = torch.full((256, N), float("nan"), device="cuda")
+    rc = _lib.lib().lush_tc_selftest_pair(ctypes.c_void_p(a_blob.data_ptr()), ctypes.c_void_p(b_blob.data_ptr()),
+                                          ctypes.c_void_p(out.data_ptr()), N, K, None)
+    _lib.check(rc, "lush_tc_selftest_pair")
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 2e-3, f"CTA-pair UMMA wrong: max err {err:.3e}"

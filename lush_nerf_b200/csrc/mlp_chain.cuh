@@ -138,7 +138,8 @@ struct ChainBars {
   uint64_t a_ready[4];          // K-values [64j, 64j+64) of the activation tile are complete (8 warps)
   uint64_t d_ready[2];          // accumulator d complete (one commit per issuer)
   uint64_t d_free[2];           // accumulator d is in the epilogue warps' registers (8 warps)
-  uint64_t first_issued;        // issuer 0 has issued block 0 of the current step (the one that overwrites D)
+  uint64_t issued[2];           // issuer i has issued one more of its blocks: block k of a step enters the tensor pipe
+                                // after block k-1 (the other issuer's), so every accumulator sums its K slices in ONE order
   uint64_t pro_ready[2];        // prologue operands of tile parity b are in shared memory (4 warps)
   uint64_t enc_free;            // the single ENC tile is no longer read by this tile's MMAs (commit)
   uint64_t pro_free[2];         // ENCV / X16 tiles of parity b are no longer read (commit)
@@ -153,7 +154,7 @@ __device__ __forceinline__ void chain_init_bars(ChainBars& B) {
     mbar_init(&B.pro_ready[r], 4); mbar_init(&B.pro_free[r], 1);
   }
   mbar_init(&B.enc_free, 1);
-  mbar_init(&B.first_issued, 1);
+  mbar_init(&B.issued[0], 1); mbar_init(&B.issued[1], 1);
   mbar_init(&B.aux, 4);
   fence_barrier_init();
 }
@@ -232,7 +233,7 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
   uint32_t stage = 0, phase = 0;
   uint32_t a_par = 0;                    // parity of the next a_ready phase (all four groups advance together)
   uint32_t dfree_phase = 0, d_uses = 0;  // bit d: parity to wait for on d_free[d]; d_uses: accumulators used so far
-  uint32_t tok_phase = 0, acc_sel = 0;
+  uint32_t tok_par = 0, acc_sel = 0;      // tok_par: parity of the next unobserved phase of the OTHER issuer's token
   const uint32_t sbase = smem_u32(smem);
   const uint32_t hi128 = desc_hi(128u);
   constexpr uint32_t A_K16 = (2u * TROWS * 16u) >> 4;   // start-address units per 16 columns of a 128-row blob
@@ -262,8 +263,10 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
         }
         if (i == 0) {                          // overwrites accumulator acc_sel: its previous epilogue must have drained it
           if (d_uses >= 2u) mbar_wait(&B.d_free[acc_sel], (dfree_phase >> acc_sel) & 1u);
-        } else if (i == 1) {                   // must not overtake block 0 in the tensor pipe
-          mbar_wait(&B.first_issued, tok_phase);
+        }
+        if (i > 0) {                           // must not overtake block i-1 (the other issuer's) in the tensor pipe:
+          mbar_wait(&B.issued[my ^ 1u], tok_par);   // fp32 accumulation order = block order, run after run
+          tok_par ^= 1u;
         }
         const bool last_blk = (i + 1u == nblk);                // probes 12..15: the step's last block
         if (last_blk) chain_trace(P, it, s, 12);
@@ -284,8 +287,8 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
           }
           if (has_h) mma_ss<4>(tacc, act_lo + grp * 4u * A_K16, b_lo, hi128, A_K16, B_K16, idesc, acc);
           umma_commit(&B.empty[stage]);
+          mbar_arrive(&B.issued[my]);
           if (i == 0) {
-            mbar_arrive(&B.first_issued);
             if (S.free_enc == 1) umma_commit(&B.enc_free);
             else if (S.free_enc == 2) umma_commit(&B.pro_free[b]);
           }
@@ -299,8 +302,12 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
           if (!((seen >> j) & 1u)) mbar_wait(&B.a_ready[j], a_par);
         a_par ^= 1u;
       }
-      if (my == 1u && nblk < 2) mbar_wait(&B.first_issued, tok_phase);
-      tok_phase ^= 1u;
+      // the other issuer's last block of this step has no successor of mine inside the step when it is the step's last
+      // block: observe its token here (every phase of a barrier is observed exactly once by its one waiter)
+      if (((nblk & 1u) != 0u) == (my == 1u)) {
+        mbar_wait(&B.issued[my ^ 1u], tok_par);
+        tok_par ^= 1u;
+      }
       if (elect_one()) umma_commit(&B.d_ready[acc_sel]);
       if (d_uses >= 2u) dfree_phase ^= (1u << acc_sel);
       ++d_uses;

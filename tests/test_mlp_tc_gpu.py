@@ -266,3 +266,46 @@ def test_tc_backward_other_topologies(D, skip, need_in):
         assert _rel(g1, g0) <= tol, (D, skip, name, _rel(g1, g0))
     if need_in:
         assert _rel(res[1][2][:, 0:6], res[0][2][:, 0:6]) <= 8e-2
+
+
+def test_tc_full_size_row_independence_and_gradient_additivity():
+    """BASELINE configs[1] size (5120 rays x 128 fine samples = 655 360 samples, 35 tiles per CTA), no oracle in the
+    loop: (i) rows are independent -- the batch evaluated in reversed ray order gives the reversed outputs BIT FOR BIT
+    (same per-row arithmetic whatever tile, CTA or accumulator buffer a row lands in); (ii) parameter gradients are
+    additive over the batch -- the gradient of the whole batch equals the sum of the gradients of its two halves up to
+    fp16 rounding under (different) loss scales and fp32 atomic ordering."""
+    R, S = 5120, 128
+    nets = O.det_nets()
+    shapes = O.mlp_param_shapes(8, 256, 63, 27, 4)
+    flat = torch.cat([nets["fine"][n].reshape(-1) for n, _ in shapes]).cuda()
+    desc = _lib.MlpDesc(8, 256, 10, 4, 4, 0)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    rb = torch.zeros(R, 11, device="cuda")
+    rb[:, :3] = torch.rand(R, 3, device="cuda", generator=g) * 2 - 1
+    rb[:, 3:6] = torch.randn(R, 3, device="cuda", generator=g) * 0.3
+    rb[:, 8:11] = torch.nn.functional.normalize(torch.randn(R, 3, device="cuda", generator=g), dim=-1)
+    z = torch.rand(R, S, device="cuda", generator=g).sort(-1)[0]
+    gout = torch.randn(R, S, 4, device="cuda", generator=g)
+
+    def run(rows, with_grad):
+        views, off = [], 0
+        fl = flat.clone()
+        for _, shp in shapes:
+            n = int(np.prod(shp)); views.append(fl[off:off + n].view(shp).requires_grad_(with_grad)); off += n
+        out = ops.mlp_apply(rb[rows].contiguous(), z[rows].contiguous(), desc, 1, fl, views)
+        if with_grad:
+            out.backward(gout[rows].contiguous())
+        return out.detach(), [v.grad for v in views]
+
+    everything = torch.arange(R, device="cuda")
+    with torch.no_grad():
+        fwd, _ = run(everything, False)
+        rev, _ = run(everything.flip(0), False)
+    assert torch.isfinite(fwd).all()
+    assert torch.equal(rev.flip(0), fwd)
+    out_t, g_all = run(everything, True)
+    assert torch.equal(out_t, fwd)                       # the training kernel (stash written) computes the same values
+    _, g_a = run(everything[:R // 2], True)
+    _, g_b = run(everything[R // 2:], True)
+    for (name, _), ga, gb, gw in zip(shapes, g_a, g_b, g_all):
+        assert _rel(ga + gb, gw) <= 5e-3, (name, _rel(ga + gb, gw))

@@ -40,7 +40,8 @@ def _worker(rank, world, port, q):
         lush_loss(out, out, y[lo:hi]).backward()
         params = list(net.parameters()) + list(unused.parameters())
         FlatGradAllReduce(params)()
-        q.put((rank, [p.grad.clone() if p.grad is not None else None for p in params]))
+        # numpy copies travel by value: a torch tensor in a Queue is a shared-memory handle that dies with this process
+        q.put((rank, [p.grad.numpy().copy() if p.grad is not None else None for p in params]))
     finally:
         dist.destroy_process_group()
 
@@ -58,7 +59,8 @@ def test_sharded_step_matches_global_batch():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=120) for _ in range(world))
+    results = {r: [None if a is None else torch.from_numpy(a) for a in arrs]
+               for r, arrs in (q.get(timeout=120) for _ in range(world))}
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

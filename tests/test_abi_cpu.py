@@ -6,6 +6,7 @@ import os
 import re
 import types
 
+import numpy as np
 import pytest
 import torch
 
@@ -130,3 +131,38 @@ def test_forward_asserts_like_the_reference():
     m.eval()
     with pytest.raises(AssertionError, match="specify poses"):
         m(4, 6, None, poses=None, render_kwargs={})
+
+
+def test_motion_plan_layer_program_host_side():
+    """The layer program handed to lush_rbk_motion_{fwd,bwd} (ops.MotionPlan) for the poster blur kernel and for a
+    topology with a skip concat -- pure host logic, no kernel call."""
+    from lush_nerf_b200.models.lushnerf import RBK
+
+    def make(D, W, skips, C):
+        return RBK(num_img=7, view_embed_ch=C, D_rbk=D, W_rbk=W, skips_rbk=skips, num_motion_rbk=4, D_rbk_r=1, W_rbk_r=32,
+                   output_ch_rbk_r=3, D_rbk_v=1, W_rbk_v=32, output_ch_rbk_v=3, D_rbk_w=1, W_rbk_w=32,
+                   rbk_se_rv_window=0.1, use_dpnerf=True, rbk_use_origin=True, near=0.0, far=1.0, ndc=True).RBK
+    plan = make(4, 64, [4], 64)._motion_plan()
+    assert plan is not None and len(plan.layers) == 10 and plan.width == 64 + 4 * 64 + 3 * 32 + 12 + 12 + 5
+    assert [seg for _, seg, _ in plan.layers][:4] == [(64, 64), (128, 64), (192, 64), (256, 64)]
+    assert all(inp == [(256, 64)] for inp, _, _ in (plan.layers[4], plan.layers[6], plan.layers[8]))   # three branches
+    assert [plan.layers[plan.heads[k]][1][1] for k in ("r", "v", "w")] == [12, 12, 5]
+    assert [relu for _, _, relu in plan.layers] == [True] * 5 + [False, True, False, True, False]
+    assert len(plan.params) == 20
+    rbk = make(3, 48, [0], 16)
+    plan = rbk._motion_plan()
+    assert plan.layers[1][0] == [(0, 16), (16, 48)]        # layer 1 reads the concat [e, h] (reference :51-52, :125-126)
+    assert plan.layers[1][1] == (64, 48)
+    assert rbk._motion_plan() is plan                      # cached while the parameters are the same objects
+
+
+def test_trainer_without_cuda_uses_torch_adam_and_cuda_only_optimizer_raises():
+    from lush_nerf_b200.optim import Adam
+    from lush_nerf_b200.train import Trainer
+    m = make_model()
+    tr = Trainer(m, 40, 60, np.eye(3), lrate=1e-3)
+    assert type(tr.optimizer) is torch.optim.Adam and len(tr.optimizer.param_groups) == 2
+    with pytest.raises(RuntimeError):
+        tr.enable_cuda_graph({"rays": torch.zeros(1, 3, 2)})
+    with pytest.raises(RuntimeError):
+        Adam(list(m.parameters())[:2], lr=1e-3)

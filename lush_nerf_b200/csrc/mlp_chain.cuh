@@ -6,7 +6,7 @@
 //     core works on step s+1 while the epilogue warps are still draining step s;
 //   * the fp16 activations that feed the next step live in ONE shared-memory tile [128 x 256] in the UMMA
 //     operand layout (no hazard: the epilogue of step s starts only after every MMA of step s has completed);
-//   * the rest of shared memory is a ring (3 x 40 KB) of weight blocks [N x 64 K] streamed with bulk async
+//   * the rest of shared memory is a ring (ChRing: 3 x 40 KB forward, 4 x 32 KB dgrad) of weight blocks [N x 64 K] streamed with bulk async
 //     copies (TMA engine) in exactly the order the MMAs consume them; the bias rides in the MMA as one extra
 //     K=16 slice against a constant ones column.
 // Hand-off between steps is per 64 K-values: the eight epilogue warps drain the accumulator 64 columns at a time
@@ -25,7 +25,7 @@
 //   warps 8-11    epilogue warpgroup 1  (columns [32,64) of every group)
 //   warp 12       weight producer (one lane)
 //   warps 14, 15  MMA issuers (converged warps, one elected lane issues): warp 14+i issues blocks i, i+2, ... of
-//                 every step; block 0 (the one that overwrites the accumulator) is ordered first by a token.
+//                 every step; tokens (ChainBars::issued) make the blocks of a step enter the tensor pipe in order.
 //                 Warp 14 also owns the TMEM allocation.
 // The SM's warp arbiter favours the highest warp id among eligible warps: the latency-critical single-thread
 // issuers sit at the top, the ALU-heavy but latency-tolerant encoder warps at the bottom.

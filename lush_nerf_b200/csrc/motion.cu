@@ -352,11 +352,9 @@ extern "C" int lush_rbk_motion_fwd(const lush_motion_net* net, const float* embe
   if (stage_w) smem += wbytes;
   LUSH_REQUIRE(smem <= 200 * 1024, "rbk_motion_fwd: activation row of %d floats does not fit shared memory",
                net->row_width);
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per call: function attributes are per device, and a process may drive several (DataParallel-style callers)
     cudaError_t e = cudaFuncSetAttribute(motion_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     LUSH_REQUIRE(e == cudaSuccess, "rbk_motion_fwd: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   unsigned blocks = (unsigned)ceil_div(n_img, MOTION_ROWS);
   motion_fwd_kernel<<<blocks, MOTION_THREADS, smem, (cudaStream_t)stream>>>(*net, embed, n_img, images_idx, N, rows,
@@ -379,11 +377,9 @@ extern "C" int lush_rbk_motion_bwd(const lush_motion_net* net, int n_img, const 
   if (stage_w) smem += wbytes;
   LUSH_REQUIRE(smem <= 200 * 1024, "rbk_motion_bwd: activation row of %d floats does not fit shared memory",
                net->row_width);
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per call: function attributes are per device, and a process may drive several (DataParallel-style callers)
     cudaError_t e = cudaFuncSetAttribute(motion_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     LUSH_REQUIRE(e == cudaSuccess, "rbk_motion_bwd: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   unsigned blocks = (unsigned)ceil_div(n_img, MOTION_ROWS);
   motion_bwd_kernel<<<blocks, MOTION_THREADS, smem, (cudaStream_t)stream>>>(*net, n_img, images_idx, N, rows, g_r,

@@ -43,8 +43,12 @@ constexpr int CH_MAX_NSTAGE = 4;
 //            stages as blocks per step, block j of a step reuses the stage of block j of the PREVIOUS step, so every
 //            copy is requested a whole step ahead (the copies take ~3 000 cycles under load; with 3 stages the last
 //            block of every step arrived ~2 000 cycles after its activations were ready)
-template <int NSTAGE_, int STAGE_BYTES_>
+template <int NSTAGE_, int STAGE_BYTES_, bool ACT_IN_TMEM_ = false>
 struct ChRing {
+  // true: the epilogue writes the next step's A operand into TENSOR memory (in place, into the first 128 columns of the
+  // accumulator it has just drained) and the hidden-block MMAs read it from there (TS mode): no activation stores /
+  // operand reads / proxy fences on the shared-memory port, which is the contended resource of these kernels
+  static constexpr bool ACT_IN_TMEM = ACT_IN_TMEM_;
   static constexpr int NSTAGE = NSTAGE_;
   static constexpr int STAGE_BYTES = STAGE_BYTES_;
   static constexpr int STAGE0 = 0;
@@ -52,7 +56,7 @@ struct ChRing {
   static constexpr int FREE0 = ACT + 128 * 256 * 2;                  // kernel-specific operands from here (see ChainMap)
   static_assert(NSTAGE_ >= 2 && NSTAGE_ <= CH_MAX_NSTAGE, "ring depth");
 };
-using FwdRing = ChRing<3, 256 * (64 + 16) * 2>;
+using FwdRing = ChRing<3, 256 * (64 + 16) * 2, true>;
 using DgradRing = ChRing<4, 256 * 64 * 2>;
 constexpr int CH_MAX_STEPS = kMaxDepth + 6;
 constexpr int CH_WG_PRO = 0;                   // first warp of the prologue warpgroup
@@ -218,6 +222,27 @@ __device__ __forceinline__ void mma_ss(uint32_t tacc, uint32_t a_lo, uint32_t b_
 #undef LUSH_SS_FIRST
 #undef LUSH_SS_NEXT
 
+// same with the A operand in tensor memory: 8 columns (16 fp16) of all 128 lanes per K=16, consecutive columns
+#define LUSH_TS_FIRST                                                       \
+  "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t.reg .b32 at, bl;\n\t"            \
+  "setp.ne.b32 p, %6, 0;\n\t"                                               \
+  "mov.b32 at, %1;\n\tmov.b32 bl, %2;\n\t"                                  \
+  "mov.b64 db, {bl, %3};\n\t"                                              \
+  "tcgen05.mma.cta_group::1.kind::f16 [%0], [at], db, %5, p;\n\t"          \
+  "setp.eq.b32 p, %6, %6;\n\t"
+#define LUSH_TS_NEXT                                                        \
+  "add.u32 at, at, 8;\n\tadd.u32 bl, bl, %4;\n\t"                           \
+  "mov.b64 db, {bl, %3};\n\t"                                              \
+  "tcgen05.mma.cta_group::1.kind::f16 [%0], [at], db, %5, p;\n\t"
+__device__ __forceinline__ void mma_ts4(uint32_t tacc, uint32_t a_tmem, uint32_t b_lo, uint32_t hi, uint32_t bk16,
+                                        uint32_t idesc, uint32_t acc) {
+  asm volatile(LUSH_TS_FIRST LUSH_TS_NEXT LUSH_TS_NEXT LUSH_TS_NEXT "}" ::"r"(tacc), "r"(a_tmem), "r"(b_lo), "r"(hi),
+               "r"(bk16), "r"(idesc), "r"(acc)
+               : "memory");
+}
+#undef LUSH_TS_FIRST
+#undef LUSH_TS_NEXT
+
 // one lane of a converged warp (the same lane every time for a full warp)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -285,7 +310,12 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
             if (S.enc_slices == 2) { mma_ss<4>(tacc, e_lo, b_lo, hi128, A_K16, B_K16, idesc, acc); acc = 1; b_lo += 4u * B_K16; }
             else if (S.enc_slices == 1) { mma_ss<2>(tacc, e_lo, b_lo, hi128, A_K16, B_K16, idesc, acc); acc = 1; b_lo += 2u * B_K16; }
           }
-          if (has_h) mma_ss<4>(tacc, act_lo + grp * 4u * A_K16, b_lo, hi128, A_K16, B_K16, idesc, acc);
+          if (has_h) {
+            if (R::ACT_IN_TMEM)   // A = packed activations in the first 128 columns of the OTHER accumulator buffer
+              mma_ts4(tacc, tmem_base + (acc_sel ^ 1u) * 256u + grp * 32u, b_lo, hi128, B_K16, idesc, acc);
+            else
+              mma_ss<4>(tacc, act_lo + grp * 4u * A_K16, b_lo, hi128, A_K16, B_K16, idesc, acc);
+          }
           umma_commit(&B.empty[stage]);
           mbar_arrive(&B.issued[my]);
           if (i == 0) {
@@ -320,6 +350,14 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
 // epilogue side of the hand-off: this warp's st.shared into columns [64j, 64j+64) of the activation tile are done
 __device__ __forceinline__ void chain_publish(ChainBars& B, int j, int lane) {
   fence_proxy_async();
+  __syncwarp();
+  mbar_arrive_if(&B.a_ready[j], lane == 0);
+}
+// the same hand-off when the activations went to tensor memory (tcgen05.st): no proxy fence, the stores are ordered
+// before the arrive by wait::st + the tcgen05 fence
+__device__ __forceinline__ void chain_publish_tmem(ChainBars& B, int j, int lane) {
+  tmem_st_wait();
+  tc_fence_before();
   __syncwarp();
   mbar_arrive_if(&B.a_ready[j], lane == 0);
 }

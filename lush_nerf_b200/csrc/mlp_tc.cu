@@ -241,7 +241,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
     const int row = 32 * (warp & 3) + lane;           // TMEM lane == tile row (a warp may only touch lanes 32*(warp%4)..)
     const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
     const bool tracer = (warp == CH_WG_EPI0 + 4 * g);
-    uint8_t* act = smem + FwdRing::ACT;
+    (void)FwdRing::ACT;   // the activation tile of the ring layout is unused here: activations live in tensor memory
     const float4* wa4 = reinterpret_cast<const float4*>(sparams + P.w_alpha_off);
     const float4* wr4 = reinterpret_cast<const float4*>(sparams + P.w_rgb_off);
     uint32_t d_phase = 0, aux_phase = 0, acc_sel = 0;   // d_phase: bit per accumulator
@@ -268,6 +268,8 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
             uint32_t (&r)[32] = hb ? rb2 : ra;
             const int col = 64 * rd + 32 * g;         // first output column of my chunk
             tmem_ld_wait();
+            // warps w of the two warpgroups own the same 32 rows: both have round rd in registers from here on
+            if (S_.writes_a) named_bar_sync(1 + (warp & 3), 64);
             if (rd + 1 < nround) tmem_ld32(tacc + 64u * (rd + 1), hb ? ra : rb2);
             else {                                    // everything of mine is in registers
               chain_release_acc(B, (int)acc_sel, lane);
@@ -277,11 +279,11 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               // critical path first: fp16 -> activation tile -> publish; everything else rides behind the hand-off
               if (S_.epi == FE_FEATURE) pack_chunk<false>(r, pw);
               else pack_chunk<true>(r, pw);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(act + ((col >> 3) + q) * (TROWS * 16) + row * 16) =
-                    make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
-              chain_publish(B, rd, lane);
+              // A operand of the next step: 16 packed columns into the accumulator buffer being drained, at
+              // columns [32 rd + 16 g, +16) -- accumulator columns that were loaded in a round <= rd (the pair barrier
+              // above covers the one case where the partner warp of the other warpgroup loaded them, round 0)
+              tmem_st16(tmem_base + tlane + acc_sel * 256u + 32u * rd + 16u * g, pw);
+              chain_publish_tmem(B, rd, lane);
               if (tracer && (rd >> 1) == g) chain_trace(C, it, s, 6 + 4 * g + (rd & 1));
               if (TRAIN) {
                 store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);

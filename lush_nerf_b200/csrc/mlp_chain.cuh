@@ -4,9 +4,11 @@
 // activations never leave the SM:
 //   * accumulators are DOUBLE-BUFFERED in tensor memory (2 x 256 fp32 columns, alternating by step): the tensor
 //     core works on step s+1 while the epilogue warps are still draining step s;
-//   * the fp16 activations that feed the next step live in ONE shared-memory tile [128 x 256] in the UMMA
-//     operand layout (no hazard: the epilogue of step s starts only after every MMA of step s has completed);
-//   * the rest of shared memory is a ring (ChRing: 3 x 40 KB forward, 4 x 32 KB dgrad) of weight blocks [N x 64 K] streamed with bulk async
+//   * the fp16 activations that feed the next step live in ONE tile [128 x 256]: in the forward kernel in TENSOR
+//     memory (written in place into the first 128 columns of the accumulator just drained, read by TS-mode MMAs),
+//     in dgrad in shared memory in the UMMA operand layout (no hazard either way: the epilogue of step s starts
+//     only after every MMA of step s has completed);
+//   * the rest of shared memory is a ring (ChRing: 4 x 40 KB forward, 4 x 32 KB dgrad) of weight blocks [N x 64 K] streamed with bulk async
 //     copies (TMA engine) in exactly the order the MMAs consume them; the bias rides in the MMA as one extra
 //     K=16 slice against a constant ones column.
 // Hand-off between steps is per 64 K-values: the eight epilogue warps drain the accumulator 64 columns at a time
@@ -38,7 +40,8 @@ namespace lush {
 constexpr int CH_THREADS = 512;
 constexpr int CH_MAX_NSTAGE = 4;
 // Weight ring, chosen per kernel (template parameter R of the producer / issuer):
-//   forward: 3 stages x 40 KB -- a [256 x 64] weight block + the [256 x 16] bias block ride in one stage
+//   forward: 4 stages x 40 KB -- a [256 x 64] weight block + the [256 x 16] bias block ride in one stage (the
+//            forward kernel keeps its activations in tensor memory, so the 64 KB activation tile is not allocated)
 //   dgrad:   4 stages x 32 KB -- no bias slices on the trunk steps and ~30 KB of spare shared memory: with as many
 //            stages as blocks per step, block j of a step reuses the stage of block j of the PREVIOUS step, so every
 //            copy is requested a whole step ahead (the copies take ~3 000 cycles under load; with 3 stages the last
@@ -53,10 +56,10 @@ struct ChRing {
   static constexpr int STAGE_BYTES = STAGE_BYTES_;
   static constexpr int STAGE0 = 0;
   static constexpr int ACT = STAGE0 + NSTAGE_ * STAGE_BYTES_;        // [128 x 256] activations (A operand)
-  static constexpr int FREE0 = ACT + 128 * 256 * 2;                  // kernel-specific operands from here (see ChainMap)
+  static constexpr int FREE0 = ACT + (ACT_IN_TMEM_ ? 0 : 128 * 256 * 2);   // kernel-specific operands from here (ChainMap)
   static_assert(NSTAGE_ >= 2 && NSTAGE_ <= CH_MAX_NSTAGE, "ring depth");
 };
-using FwdRing = ChRing<3, 256 * (64 + 16) * 2, true>;
+using FwdRing = ChRing<4, 256 * (64 + 16) * 2, true>;   // the 64 KB activation tile is gone: one more 40 KB stage
 using DgradRing = ChRing<4, 256 * 64 * 2>;
 constexpr int CH_MAX_STEPS = kMaxDepth + 6;
 constexpr int CH_WG_PRO = 0;                   // first warp of the prologue warpgroup

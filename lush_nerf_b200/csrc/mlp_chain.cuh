@@ -4,10 +4,10 @@
 // activations never leave the SM:
 //   * accumulators are DOUBLE-BUFFERED in tensor memory (2 x 256 fp32 columns, alternating by step): the tensor
 //     core works on step s+1 while the epilogue warps are still draining step s;
-//   * the fp16 activations that feed the next step live in ONE tile [128 x 256]: in the forward kernel in TENSOR
-//     memory (written in place into the first 128 columns of the accumulator just drained, read by TS-mode MMAs),
-//     in dgrad in shared memory in the UMMA operand layout (no hazard either way: the epilogue of step s starts
-//     only after every MMA of step s has completed);
+//   * the fp16 activations that feed the next step live in ONE tile [128 x 256] in TENSOR memory (written in place
+//     into the first 128 columns of the accumulator just drained, read by TS-mode MMAs; no hazard: the epilogue of
+//     step s starts only after every MMA of step s has completed).  ChRing::ACT_IN_TMEM = false selects the older
+//     shared-memory activation tile in the UMMA operand layout;
 //   * the rest of shared memory is a ring (ChRing: 4 x 40 KB forward, 4 x 32 KB dgrad) of weight blocks [N x 64 K] streamed with bulk async
 //     copies (TMA engine) in exactly the order the MMAs consume them; the bias rides in the MMA as one extra
 //     K=16 slice against a constant ones column.
@@ -60,7 +60,7 @@ struct ChRing {
   static_assert(NSTAGE_ >= 2 && NSTAGE_ <= CH_MAX_NSTAGE, "ring depth");
 };
 using FwdRing = ChRing<4, 256 * (64 + 16) * 2, true>;   // the 64 KB activation tile is gone: one more 40 KB stage
-using DgradRing = ChRing<4, 256 * 64 * 2>;
+using DgradRing = ChRing<4, 256 * 64 * 2, true>;
 constexpr int CH_MAX_STEPS = kMaxDepth + 6;
 constexpr int CH_WG_PRO = 0;                   // first warp of the prologue warpgroup
 constexpr int CH_WG_EPI0 = 4;                  // first warp of epilogue warpgroup 0
@@ -89,6 +89,8 @@ struct ChainStep {
   int8_t writes_a;    // 1: the epilogue writes the activation tile (and publishes its 64-column groups)
   int8_t free_enc;    // after this step's block 0: 1 = ENC, 2 = ENCV / X16 of this tile are no longer read
   int8_t epi;         // kernel-specific epilogue kind
+  int8_t keep_acc;    // 1: the NEXT step uses the same accumulator buffer again (its A operand, produced two steps ago,
+                      //    lives in the other one); 0: the buffers alternate
   int16_t p0, p1;     // epilogue parameters
   int32_t off0, off1; // epilogue byte offsets
 };
@@ -260,7 +262,7 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
                                                  const ChainMap map, int64_t ntiles, const uint32_t my) {
   uint32_t stage = 0, phase = 0;
   uint32_t a_par = 0;                    // parity of the next a_ready phase (all four groups advance together)
-  uint32_t dfree_phase = 0, d_uses = 0;  // bit d: parity to wait for on d_free[d]; d_uses: accumulators used so far
+  uint32_t n_used0 = 0, n_used1 = 0;     // how often each accumulator buffer has been written so far
   uint32_t tok_par = 0, acc_sel = 0;      // tok_par: parity of the next unobserved phase of the OTHER issuer's token
   const uint32_t sbase = smem_u32(smem);
   const uint32_t hi128 = desc_hi(128u);
@@ -290,7 +292,8 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
           continue;
         }
         if (i == 0) {                          // overwrites accumulator acc_sel: its previous epilogue must have drained it
-          if (d_uses >= 2u) mbar_wait(&B.d_free[acc_sel], (dfree_phase >> acc_sel) & 1u);
+          const uint32_t used = acc_sel ? n_used1 : n_used0;
+          if (used) mbar_wait(&B.d_free[acc_sel], (used - 1u) & 1u);
         }
         if (i > 0) {                           // must not overtake block i-1 (the other issuer's) in the tensor pipe:
           mbar_wait(&B.issued[my ^ 1u], tok_par);   // fp32 accumulation order = block order, run after run
@@ -342,9 +345,8 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
         tok_par ^= 1u;
       }
       if (elect_one()) umma_commit(&B.d_ready[acc_sel]);
-      if (d_uses >= 2u) dfree_phase ^= (1u << acc_sel);
-      ++d_uses;
-      acc_sel ^= 1u;
+      if (acc_sel) ++n_used1; else ++n_used0;
+      if (!S.keep_acc) acc_sel ^= 1u;
       chain_trace(P, it, s, 2 * (int)my + 1);
     }
   }

@@ -29,7 +29,7 @@ static void make_fwd_chain(const MlpLayout& L, const FwdPlan& P, ChainPlan& C) {
     const bool enc = (i == 0) || (L.skip >= 0 && i == L.skip + 1);
     s.enc_slices = enc ? 2 : 0;
     s.h_slices = (i == 0) ? 0 : TW / KS;
-    s.wait_a = (i > 0); s.writes_a = 1;
+    s.wait_a = (i > 0); s.writes_a = 1; s.keep_acc = 0;
     s.free_enc = (L.skip >= 0 ? (i == L.skip + 1) : (i == 0)) ? 1 : 0;   // last step that reads gamma(x)
     s.epi = (i == L.D - 1) ? FE_TRUNK_LAST : FE_TRUNK;
     s.p0 = (int16_t)i; s.p1 = 0;
@@ -39,12 +39,12 @@ static void make_fwd_chain(const MlpLayout& L, const FwdPlan& P, ChainPlan& C) {
   }
   { ChainStep& s = C.steps[n];
     s.N = TW; s.pre16 = 1; s.enc_src = 0; s.enc_slices = 0; s.h_slices = TW / KS;
-    s.wait_a = 1; s.writes_a = 1; s.free_enc = 0;
+    s.wait_a = 1; s.writes_a = 1; s.free_enc = 0; s.keep_acc = 0;
     s.epi = FE_FEATURE; s.p0 = 0; s.p1 = 0; s.off0 = P.rec_feat; s.off1 = 0;
     ++n; }
   { ChainStep& s = C.steps[n];
     s.N = 128; s.pre16 = 1; s.enc_src = 1; s.enc_slices = 1; s.h_slices = TW / KS;
-    s.wait_a = 1; s.writes_a = 0; s.free_enc = 2;
+    s.wait_a = 1; s.writes_a = 0; s.free_enc = 2; s.keep_acc = 0;
     s.epi = FE_VIEWS; s.p0 = 0; s.p1 = 0; s.off0 = P.rec_hv; s.off1 = P.rec_maskv;
     ++n; }
   C.nsteps = n;
@@ -250,7 +250,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
       const int64_t m = tile * TROWS + row;
       uint8_t* rec = TRAIN ? stash + tile * (int64_t)P.rec_bytes : nullptr;
       float alpha = 0.f;
-      for (int s = 0; s < C.nsteps; ++s, acc_sel ^= 1u) {
+      for (int s = 0; s < C.nsteps; ++s, acc_sel ^= 1u) {   // the forward plan never keeps an accumulator (keep_acc = 0)
         const ChainStep S_ = C.steps[s];
         const int nround = S_.N >> 6;                 // 64-column groups: 256 -> 4, 128 -> 2
         mbar_wait(&B.d_ready[acc_sel], (d_phase >> acc_sel) & 1u); d_phase ^= (1u << acc_sel);

@@ -58,6 +58,7 @@ static void make_bwd_chain(const MlpLayout& L, bool need_in, ChainPlan& C, BwdPl
     ChainStep& s = C.steps[n];
     s.N = (int16_t)N; s.pre16 = (int8_t)pre16; s.enc_slices = 0; s.enc_src = 0; s.h_slices = (int8_t)h_slices;
     s.wait_a = (int8_t)wait_a; s.writes_a = (int8_t)writes_a; s.free_enc = (int8_t)free_enc; s.epi = (int8_t)epi;
+    s.keep_acc = 0;
     s.p0 = (int16_t)p0; s.p1 = 0; s.off0 = off0; s.off1 = 0;
     BPackJob& J = K.jobs[n];
     J.out_off = off; J.w_off = w_off; J.fan_in = fan_in; J.col0 = col0; J.ncols_real = ncols_real; J.N = N;
@@ -73,6 +74,7 @@ static void make_bwd_chain(const MlpLayout& L, bool need_in, ChainPlan& C, BwdPl
     const bool is_skip = (L.skip >= 0 && l == L.skip + 1);
     if (is_skip && need_in) {
       add(64, 0, 8, prev_wrote, 0, 0, BE_ENC, 0, 0, L.pts_w[l], L.pts_in[l], 0, L.in_ch, 0, 0);
+      C.steps[n - 1].keep_acc = 1;   // the next trunk step reads the same dZ (tensor memory of the OTHER buffer) again
       prev_wrote = 0;
       B.has_skip_enc = 1;
     }
@@ -209,7 +211,6 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
     const int g = (warp - CH_WG_EPI0) >> 2;
     const int row = 32 * (warp & 3) + lane;
     const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
-    uint8_t* act = smem + DgradRing::ACT;
     uint32_t d_phase = 0, acc_sel = 0;
     uint4 mnext = make_uint4(0u, 0u, 0u, 0u);
     if ((int64_t)blockIdx.x < ntiles)
@@ -219,7 +220,7 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint8_t* frec = fstash + tile * (int64_t)P.rec_bytes;
       uint8_t* grec = gstash + tile * (int64_t)Bp.grec_bytes;
-      for (int s = 0; s < C.nsteps; ++s, acc_sel ^= 1u) {
+      for (int s = 0; s < C.nsteps; ++s) {
         const ChainStep S_ = C.steps[s];
         const int nround = S_.N >> 6;
         // the ReLU bits of my columns (one word per round) were requested one step ago (DRAM latency ~1 us)
@@ -242,6 +243,8 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
               uint32_t (&r)[32] = hb ? rb2 : ra;
               const int col = 64 * rd + 32 * g;
               tmem_ld_wait();
+              // warps w of the two warpgroups own the same 32 rows: both have round rd in registers from here on
+              if (S_.writes_a) named_bar_sync(1 + (warp & 3), 64);
               if (rd + 1 < nround) tmem_ld32(tacc + 64u * (rd + 1), hb ? ra : rb2);
               else {
                 chain_release_acc(B, (int)acc_sel, lane);
@@ -261,11 +264,9 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
               }
               if (S_.epi != BE_ENC) {
                 if (S_.writes_a) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(act + ((col >> 3) + q) * (TROWS * 16) + row * 16) =
-                        make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
-                  chain_publish(B, rd, lane);
+                  // A operand of the next step(s): packed columns [32 rd + 16 g, +16) of the buffer being drained
+                  tmem_st16(tmem_base + tlane + acc_sel * 256u + 32u * rd + 16u * g, pw);
+                  chain_publish_tmem(B, rd, lane);
                   if (tracer && (rd >> 1) == g) chain_trace(C, it, s, 6 + 4 * g + (rd & 1));
                 }
                 store_chunk_global(grec + S_.off0, S_.N >> 3, col, row, pw);
@@ -279,6 +280,7 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
           __syncwarp();
           if (lane == 0) { mbar_arrive(&B.a_ready[2]); mbar_arrive(&B.a_ready[3]); }
         }
+        if (!S_.keep_acc) acc_sel ^= 1u;
       }
     }
   }

@@ -144,6 +144,38 @@ def cpu_reference_run(steps, warmup, n_pixels=32):
     return R * len(times) / total, 1e3 * total / len(times), cores, sample
 
 
+def render_leg(args, model, trainer, ops, mlp_events, dev, local):
+    """ms/frame of NeRFAll.forward in eval mode over a spiral path (rays generated from the pose on the device)."""
+    from lush_nerf_b200.synthetic import spiral_poses
+    poses = torch.from_numpy(spiral_poses(args.render_frames + 2, radius_scale=2.0)).to(dev)
+    rk = dict(perturb=False, N_importance=N_IMPORTANCE, N_samples=N_SAMPLES, use_viewdirs=True, white_bkgd=False,
+              raw_noise_std=0.0, inference=True, near=0.0, far=1.0)
+    model.eval()
+    with torch.no_grad():
+        model(H, W, trainer.K, chunk=1024 * 32, poses=poses[:2], render_kwargs=dict(rk))   # warm-up frames
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rsampler = ClockSampler(local)
+        rsampler.start()
+        mlp_events.clear()
+        ops.MLP_EVENT_SINK = mlp_events
+        try:
+            r0.record()
+            rgbs, _, _ = model(H, W, trainer.K, chunk=1024 * 32, poses=poses[2:], render_kwargs=dict(rk))
+            r1.record()
+            torch.cuda.synchronize()
+        finally:
+            ops.MLP_EVENT_SINK = None
+    rclocks = rsampler.stop()
+    ms_frame = r0.elapsed_time(r1) / args.render_frames
+    mlp_ms_frame = sum(a.elapsed_time(b) for lab, a, b in mlp_events if lab == "fwd") / args.render_frames
+    fl = FLOP_FWD_PER_SAMPLE * H * W * SAMPLES_PER_RAY
+    return {"ms_per_frame": ms_frame, "frames": args.render_frames, "rays_per_s": H * W / (ms_frame * 1e-3),
+            "image": f"{H}x{W}", "chunk": 32768, "mlp_ms_per_frame": mlp_ms_frame,
+            "mlp_tflops": fl / (mlp_ms_frame * 1e-3) / 1e12 if mlp_ms_frame > 0 else None,
+            "finite": bool(torch.isfinite(rgbs).all().item()), "clocks": rclocks}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -327,36 +359,10 @@ def main():
     # ---- render leg (BASELINE configs[3]): --render_only style full frames, chunk 32768, 64+64, det sampling
     render = None
     if world == 1 and not args.no_render:
-      try:   # a failure of this secondary leg must not cost the headline line
-          from lush_nerf_b200.synthetic import spiral_poses
-          poses = torch.from_numpy(spiral_poses(args.render_frames + 2, radius_scale=2.0)).to(dev)
-          rk = dict(perturb=False, N_importance=N_IMPORTANCE, N_samples=N_SAMPLES, use_viewdirs=True, white_bkgd=False,
-                    raw_noise_std=0.0, inference=True, near=0.0, far=1.0)
-          model.eval()
-          with torch.no_grad():
-              model(H, W, trainer.K, chunk=1024 * 32, poses=poses[:2], render_kwargs=dict(rk))   # warm-up frames
-              torch.cuda.synchronize()
-              r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-              rsampler = ClockSampler(local)
-              rsampler.start()
-              mlp_events.clear()
-              ops.MLP_EVENT_SINK = mlp_events
-              r0.record()
-              rgbs, _, _ = model(H, W, trainer.K, chunk=1024 * 32, poses=poses[2:], render_kwargs=dict(rk))
-              r1.record()
-              torch.cuda.synchronize()
-              ops.MLP_EVENT_SINK = None
-          rclocks = rsampler.stop()
-          ms_frame = r0.elapsed_time(r1) / args.render_frames
-          mlp_ms_frame = sum(a.elapsed_time(b) for lab, a, b in mlp_events if lab == "fwd") / args.render_frames
-          fl = FLOP_FWD_PER_SAMPLE * H * W * SAMPLES_PER_RAY
-          render = {"ms_per_frame": ms_frame, "frames": args.render_frames, "rays_per_s": H * W / (ms_frame * 1e-3),
-                    "image": f"{H}x{W}", "chunk": 32768, "mlp_ms_per_frame": mlp_ms_frame,
-                    "mlp_tflops": fl / (mlp_ms_frame * 1e-3) / 1e12 if mlp_ms_frame > 0 else None,
-                    "finite": bool(torch.isfinite(rgbs).all().item()), "clocks": rclocks}
-          model.train()
-      except Exception as e:
-        render = {"error": f"{type(e).__name__}: {e}"}
+        try:   # a failure of this secondary leg must not cost the headline line
+            render = render_leg(args, model, trainer, ops, mlp_events, dev, local)
+        except Exception as e:
+            render = {"error": f"{type(e).__name__}: {e}"}
         model.train()
 
     if rank == 0:

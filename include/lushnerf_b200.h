@@ -58,6 +58,13 @@ int lush_ray_prep_bwd(const float* rays, const float* g_ray_batch, float* g_rays
 int lush_ray_gen_prep(const float* c2w, int c2w_stride, int H, int W, double fx, double fy, double cx, double cy,
                       float near, float far, int ndc, int64_t pix0, int64_t n, float* ray_batch, void* stream);
 
+/* Raw rays of n arbitrary (view, pixel) pairs: rays[t] = (o, d) of pixel pix_idx[t] (row-major index, values in
+ * [0, H*W)) seen from poses[view_idx[t]] -- a training batch drawn on the device instead of gathered from the
+ * pre-expanded ray table (reference run_lushnerf.py:538-616 with get_rays_np, helpers:531-539).  poses: device
+ * [V, 3, 4] (pose_stride = 12) or [V, 4, 4] (16) fp32; rays [n, 3, 2] fp32 as NeRFAll.forward takes them. */
+int lush_ray_gen_gather(const float* poses, int pose_stride, const int64_t* view_idx, const int64_t* pix_idx, int H,
+                        int W, double fx, double fy, double cx, double cy, int64_t n, float* rays, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Coarse sample placement.  Replaces models/lushnerf.py:389-412 (render_rays) / :501-523:
  *   t = linspace(0,1,S) (passed in as t_vals[S], computed by the host exactly as the reference

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "lush_ray_prep_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_double, c_int, _P]),
     "lush_ray_gen_prep": (c_int, [_P, c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_float, c_float,
                                   c_int, c_int64, c_int64, _P, _P]),
+    "lush_ray_gen_gather": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_double, c_double, c_double, c_double, c_int64,
+                                    _P, _P]),
     "lush_stratified_z": (c_int, [_P, c_int, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "lush_composite_fwd": (c_int, [_P, _P, _P, c_int, _P, c_float, c_int, _P, _P, _P, _P, _P, _P, c_int64,
                                    c_int, _P]),

@@ -372,6 +372,46 @@ extern "C" int lush_ray_prep_fwd(const float* rays, float* ray_batch, int64_t R,
   return 0;
 }
 
+namespace lush {
+// Raw rays (o, d) of arbitrary (view, pixel) pairs, e.g. a training batch drawn on the device: replaces the
+// pre-expanded [V, H, W, ro+rd+rgb, 3] ray table and its host-side fancy indexing (reference run_lushnerf.py:538-616,
+// get_rays_np helpers:531-539).  rays [n, 3, 2] in the layout NeRFAll.forward takes.
+__global__ void ray_gen_gather_kernel(const float* __restrict__ poses, int pose_stride, const int64_t* __restrict__ view,
+                                      const int64_t* __restrict__ pix, PinholeConst cam, int W, int64_t n,
+                                      float* __restrict__ rays) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float* c2w = poses + view[t] * pose_stride;
+  const int64_t p = pix[t];
+  const int64_t j = p / W;
+  const float fi = (float)(p - j * W), fj = (float)j;
+  const float u = (fi + cam.ax) / cam.fx, v = -((fj + cam.ay) / cam.fy), w = -1.f;
+  float* q = rays + t * 6;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float* row = c2w + r * 4;
+    q[2 * r] = row[3];
+    q[2 * r + 1] = (u * row[0] + v * row[1]) + w * row[2];
+  }
+}
+}  // namespace lush
+
+extern "C" int lush_ray_gen_gather(const float* poses, int pose_stride, const int64_t* view_idx, const int64_t* pix_idx,
+                                   int H, int W, double fx, double fy, double cx, double cy, int64_t n, float* rays,
+                                   void* stream) {
+  LUSH_REQUIRE(poses && pose_stride >= 12 && H > 0 && W > 0 && fx != 0.0 && fy != 0.0 && n >= 0 &&
+                   (n == 0 || (view_idx && pix_idx && rays)),
+               "ray_gen_gather: bad arguments");
+  if (n == 0) return 0;
+  PinholeConst cam;
+  cam.ax = (float)(0.5 - cx); cam.ay = (float)(0.5 - cy); cam.fx = (float)fx; cam.fy = (float)fy;
+  int th = 256;
+  ray_gen_gather_kernel<<<(unsigned)ceil_div(n, th), th, 0, (cudaStream_t)stream>>>(poses, pose_stride, view_idx, pix_idx,
+                                                                                  cam, W, n, rays);
+  LUSH_LAUNCH_CHECK("ray_gen_gather");
+  return 0;
+}
+
 extern "C" int lush_ray_gen_prep(const float* c2w, int c2w_stride, int H, int W, double fx, double fy, double cx,
                                  double cy, float near, float far, int ndc, int64_t pix0, int64_t n,
                                  float* ray_batch, void* stream) {

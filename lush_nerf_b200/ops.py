@@ -82,6 +82,26 @@ def ray_gen_prep(c2w: torch.Tensor, H: int, W: int, K, near=0.0, far=1.0, ndc=Tr
     return out
 
 
+def ray_gen_gather(poses: torch.Tensor, view_idx: torch.Tensor, pix_idx: torch.Tensor, H: int, W: int, K):
+    """rays [n, 3, 2] of the (view, pixel) pairs: a training batch's rays generated on the device from the poses
+    ([V,3,4] or [V,4,4]) instead of looked up in a pre-expanded ray table (no gradient: poses are constants)."""
+    if not poses.is_cuda:
+        raise RuntimeError("lush_nerf_b200.ray_gen_gather needs CUDA tensors; there is no CPU fallback")
+    poses = _f32c(poses.detach())
+    if poses.dim() != 3 or poses.shape[1] < 3 or poses.shape[2] != 4:
+        raise ValueError(f"ray_gen_gather: poses must be [V,3,4] or [V,4,4], got {tuple(poses.shape)}")
+    view_idx, pix_idx = view_idx.reshape(-1).contiguous(), pix_idx.reshape(-1).contiguous()
+    if view_idx.numel() != pix_idx.numel():
+        raise ValueError("ray_gen_gather: view_idx and pix_idx differ in length")
+    n = view_idx.numel()
+    out = _empty((n, 3, 2), poses)
+    check(lib().lush_ray_gen_gather(ptr(poses, "poses"), poses.shape[1] * 4, ptr(view_idx, "view_idx", torch.int64),
+                                    ptr(pix_idx, "pix_idx", torch.int64), int(H), int(W), float(K[0][0]),
+                                    float(K[1][1]), float(K[0][2]), float(K[1][2]), n, ptr(out), stream()),
+          "lush_ray_gen_gather")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # coarse sample placement (reference models/lushnerf.py:389-412)
 # ------------------------------------------------------------------------------------------------

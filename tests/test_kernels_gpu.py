@@ -260,6 +260,25 @@ def test_ray_gen_prep_vs_oracle_get_rays(ndc):
         ops.ray_gen_prep(c2w.to(DEV), H, W, K, near, far, ndc, pix0=H * W - 5, n=6)
 
 
+def test_ray_gen_gather_vs_oracle_ray_table():
+    """Training-batch rays of random (view, pixel) pairs generated on the device vs the oracle's get_rays table
+    (helpers:517-528) indexed the way the reference's batching does (run_lushnerf.py:538-616)."""
+    from lush_nerf_b200.synthetic import synthetic_poses
+    H, W, f = 40, 60, 50.0
+    K = np.array([[f, 0, 0.5 * W], [0, 1.1 * f, 0.45 * H], [0, 0, 1]])
+    poses = torch.from_numpy(synthetic_poses(5, seed=2)).float()
+    table = torch.stack([torch.stack(O.get_rays(H, W, K, poses[v]), -1).reshape(-1, 3, 2) for v in range(5)])
+    g = torch.Generator().manual_seed(4)
+    view = torch.randint(0, 5, (777,), generator=g)
+    pix = torch.randint(0, H * W, (777,), generator=g)
+    out = ops.ray_gen_gather(poses.to(DEV), view.to(DEV), pix.to(DEV), H, W, K)
+    close(out, table[view, pix], 1e-6, "rays")
+    assert ops.ray_gen_gather(poses.to(DEV), view[:0].to(DEV), pix[:0].to(DEV), H, W, K).shape == (0, 3, 2)
+    p44 = torch.eye(4).repeat(5, 1, 1)
+    p44[:, :3] = poses
+    assert torch.equal(ops.ray_gen_gather(p44.to(DEV), view.to(DEV), pix.to(DEV), H, W, K), out)
+
+
 @pytest.mark.parametrize("perturb", [False, True])
 @pytest.mark.parametrize("lindisp", [False, True])
 def test_stratified_z(perturb, lindisp):

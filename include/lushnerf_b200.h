@@ -24,12 +24,24 @@
 extern "C" {
 #endif
 
-#define LUSH_ABI_VERSION 1
+#define LUSH_ABI_VERSION 2
 
 #define LUSH_OK 0
 #define LUSH_EINVAL (-1)      /* bad argument / unsupported shape */
 #define LUSH_EWORKSPACE (-2)  /* workspace too small */
 #define LUSH_EUNSUPPORTED (-3)
+
+/* Bits of the device-side error word (`flags` / `err_flag` arguments, int32, OR-ed atomically by the kernels and read
+ * lazily by the host -- the replacement of the reference's ~20 isnan/isinf host syncs per render_rays call,
+ * models/lushnerf.py:474-478, and of the index check nn.Embedding performs, :32,119):
+ *   bits 0..9   NaN (even bit) / Inf (odd bit) in rgb_map, depth_map, acc_map, density_map, raw  (lush_composite_fwd)
+ *   bit 10      an images_idx value outside [0, n_img)            (lush_rbk_motion_fwd)
+ *   bit 11      a view index outside [0, n_views)                 (lush_ray_gen_gather)
+ *   bit 12      a pixel index outside [0, H*W)                    (lush_ray_gen_gather)
+ */
+#define LUSH_FLAG_BAD_IMAGE_INDEX (1 << 10)
+#define LUSH_FLAG_BAD_VIEW_INDEX (1 << 11)
+#define LUSH_FLAG_BAD_PIXEL_INDEX (1 << 12)
 
 int lush_abi_version(void);
 const char* lush_last_error(void);
@@ -58,12 +70,21 @@ int lush_ray_prep_bwd(const float* rays, const float* g_ray_batch, float* g_rays
 int lush_ray_gen_prep(const float* c2w, int c2w_stride, int H, int W, double fx, double fy, double cx, double cy,
                       float near, float far, int ndc, int64_t pix0, int64_t n, float* ray_batch, void* stream);
 
-/* Raw rays of n arbitrary (view, pixel) pairs: rays[t] = (o, d) of pixel pix_idx[t] (row-major index, values in
- * [0, H*W)) seen from poses[view_idx[t]] -- a training batch drawn on the device instead of gathered from the
- * pre-expanded ray table (reference run_lushnerf.py:538-616 with get_rays_np, helpers:531-539).  poses: device
- * [V, 3, 4] (pose_stride = 12) or [V, 4, 4] (16) fp32; rays [n, 3, 2] fp32 as NeRFAll.forward takes them. */
-int lush_ray_gen_gather(const float* poses, int pose_stride, const int64_t* view_idx, const int64_t* pix_idx, int H,
-                        int W, double fx, double fy, double cx, double cy, int64_t n, float* rays, void* stream);
+/* A training batch staged on the device: for n (view, pixel) pairs, rays[t] = (o, d) of pixel pix_idx[t] (row-major
+ * index in [0, H*W)) seen from poses[view_idx[t]], and -- optionally -- the pixel's target colour and frequency-mask
+ * bit gathered from device-resident tables.  Replaces the pre-expanded [N, ro+rd+rgb, 3] ray table, its per-epoch
+ * host-side shuffles and the per-iteration slicing (reference run_lushnerf.py:538-616 with get_rays_np,
+ * helpers:531-539): only the two index vectors travel per step.
+ *   poses   [n_views, rows >= 3, row_stride >= 4] fp32, view v at poses + v*pose_stride, row r at + r*pose_row_stride
+ *           ([V,3,4]: 12 / 4;  [V,4,4]: 16 / 4;  the LLFF [V,3,5] block: 15 / 5)
+ *   rays    [n, 3, 2] fp32 as NeRFAll.forward takes them
+ *   images  nullable [n_views, H*W, 3] fp32 -> rgb_out [n, 3];   masks nullable [n_views, H*W] uint8 -> mask_out [n]
+ *   err_flag nullable device int32: an index outside its range is CLAMPED (no out-of-bounds read, a defined ray) and
+ *           LUSH_FLAG_BAD_VIEW_INDEX / LUSH_FLAG_BAD_PIXEL_INDEX is OR-ed into it */
+int lush_ray_gen_gather(const float* poses, int n_views, int pose_stride, int pose_row_stride, const int64_t* view_idx,
+                        const int64_t* pix_idx, int H, int W, double fx, double fy, double cx, double cy, int64_t n,
+                        float* rays, const float* images, float* rgb_out, const uint8_t* masks, uint8_t* mask_out,
+                        int* err_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Coarse sample placement.  Replaces models/lushnerf.py:389-412 (render_rays) / :501-523:
@@ -112,8 +133,12 @@ int lush_sample_pdf(const float* bins, const float* weights, const float* cdf_in
                     void* stream);
 /* Fused fine-sample placement: z_mid + sample_pdf(weights[:,1:-1]) + sort(cat(z, z_samples))
  * (models/lushnerf.py:435-440 / :544-549) + z_std (:465).  z [R,S], weights [R,S] (full weights of the
- * coarse pass).  Outputs z_fine [R,S+N] sorted ascending, z_samples [R,N], z_std [R] nullable. */
-int lush_sample_merge(const float* z, const float* weights, const float* u, int64_t u_stride,
+ * coarse pass; nullable when cdf_in is given).  cdf_in (nullable) [R,S-1]: STRICT mode as in lush_sample_pdf -- the
+ * cdf of weights[:,1:-1] computed by the caller with the reference's own ops (helpers:568-571).
+ * Outputs z_fine [R,S+N] sorted ascending, z_samples [R,N], z_std [R] nullable.
+ * Precondition: every row of z is ascending and free of NaNs (the coarse samples of render_rays are); the merge is
+ * by rank, not a full sort.  If it is violated the unfilled slots of z_fine hold NaN (never stale memory). */
+int lush_sample_merge(const float* z, const float* weights, const float* cdf_in, const float* u, int64_t u_stride,
                       float* z_fine, float* z_samples, float* z_std, int64_t R, int S, int N,
                       void* stream);
 
@@ -203,7 +228,10 @@ int lush_blend_tonemap_bwd(const float* rgb, const float* ccw, const float* nois
  * r_off / v_off / w_off are the out_off of the three head layers (act = 0, widths 3M, 3M, M+1).
  *   fwd: rows [n_img, row_width] receives the activation rows (needed by bwd); r, v [N, 3M]; ccw [N, M+1].
  *   bwd: g_r / g_v / g_ccw may be null (no gradient); gw / gb of every layer are ACCUMULATED into (zero them
- *        first); g_embed [n_img, embed_dim] is written (may be null).  images_idx values must lie in [0, n_img).
+ *        first); g_embed [n_img, embed_dim] is written (may be null).
+ * An images_idx value outside [0, n_img) (nn.Embedding raises on it): fwd gives that ray the identity kernel
+ * (r = v = 0, ccw = (1, 0, ..., 0)) and ORs LUSH_FLAG_BAD_IMAGE_INDEX into *err_flag (nullable device int32); bwd
+ * ignores the ray.
  * ------------------------------------------------------------------------------------------- */
 #define LUSH_MOTION_MAX_LAYERS 24
 typedef struct lush_dense_layer {
@@ -220,7 +248,7 @@ typedef struct lush_motion_net {
   lush_dense_layer layers[LUSH_MOTION_MAX_LAYERS];
 } lush_motion_net;
 int lush_rbk_motion_fwd(const lush_motion_net* net, const float* embed, int n_img, const int64_t* images_idx,
-                        int64_t N, float* rows, float* r, float* v, float* ccw, void* stream);
+                        int64_t N, float* rows, float* r, float* v, float* ccw, int* err_flag, void* stream);
 int lush_rbk_motion_bwd(const lush_motion_net* net, int n_img, const int64_t* images_idx, int64_t N,
                         const float* rows, const float* g_r, const float* g_v, const float* g_ccw,
                         float* g_embed, void* stream);

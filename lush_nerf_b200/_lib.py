@@ -51,15 +51,15 @@ _SIGNATURES = {
     "lush_ray_prep_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_double, c_int, _P]),
     "lush_ray_gen_prep": (c_int, [_P, c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_float, c_float,
                                   c_int, c_int64, c_int64, _P, _P]),
-    "lush_ray_gen_gather": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_double, c_double, c_double, c_double, c_int64,
-                                    _P, _P]),
+    "lush_ray_gen_gather": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_double, c_double, c_double,
+                                    c_double, c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "lush_stratified_z": (c_int, [_P, c_int, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "lush_composite_fwd": (c_int, [_P, _P, _P, c_int, _P, c_float, c_int, _P, _P, _P, _P, _P, _P, c_int64,
                                    c_int, _P]),
     "lush_composite_bwd": (c_int, [_P, _P, _P, c_int, _P, c_float, c_int, _P, _P, _P, _P, _P, _P, _P,
                                    c_int64, c_int, _P]),
     "lush_sample_pdf": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int, _P]),
-    "lush_sample_merge": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "lush_sample_merge": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "lush_mlp_param_count": (c_int64, [POINTER(MlpDesc)]),
     "lush_mlp_impl_supported": (c_int, [POINTER(MlpDesc), c_int]),
     "lush_mlp_workspace_bytes": (c_size_t, [POINTER(MlpDesc), c_int64, c_int, c_int, c_int]),
@@ -72,7 +72,7 @@ _SIGNATURES = {
     "lush_rbk_warp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "lush_blend_tonemap_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "lush_blend_tonemap_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
-    "lush_rbk_motion_fwd": (c_int, [POINTER(MotionNet), _P, c_int, _P, c_int64, _P, _P, _P, _P, _P]),
+    "lush_rbk_motion_fwd": (c_int, [POINTER(MotionNet), _P, c_int, _P, c_int64, _P, _P, _P, _P, _P, _P]),
     "lush_rbk_motion_bwd": (c_int, [POINTER(MotionNet), c_int, _P, c_int64, _P, _P, _P, _P, _P, _P]),
     "lush_blur_loss": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P]),
     "lush_adam_step": (c_int, [POINTER(AdamSeg), c_int, _P, _P, _P, c_double, c_double, c_double, _P]),
@@ -85,6 +85,9 @@ _SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 2
+# bits of the device-side error word (include/lushnerf_b200.h)
+FLAG_BAD_IMAGE_INDEX, FLAG_BAD_VIEW_INDEX, FLAG_BAD_PIXEL_INDEX = 1 << 10, 1 << 11, 1 << 12
 
 
 def exported_symbols():
@@ -105,7 +108,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
-        if handle.lush_abi_version() != 1:
+        if handle.lush_abi_version() != ABI_VERSION:
             raise RuntimeError("liblushnerf_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

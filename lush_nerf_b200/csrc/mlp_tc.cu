@@ -277,8 +277,8 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
             }
             if (S_.epi != FE_VIEWS) {
               // critical path first: fp16 -> activation tile -> publish; everything else rides behind the hand-off
-              if (S_.epi == FE_FEATURE) pack_chunk<false>(r, pw);
-              else pack_chunk<true>(r, pw);
+              if (S_.epi == FE_FEATURE) pack_chunk<false, false>(r, pw);
+              else pack_chunk<true, false>(r, pw);
               // A operand of the next step: 16 packed columns into the accumulator buffer being drained, at
               // columns [32 rd + 16 g, +16) -- accumulator columns that were loaded in a round <= rd (the pair barrier
               // above covers the one case where the partner warp of the other warpgroup loaded them, round 0)
@@ -294,10 +294,10 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                   const float4 w4 = wa4[(col >> 2) + j4];
-                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), w4.x, alpha);
-                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f), w4.y, alpha);
-                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), w4.z, alpha);
-                  alpha = fmaf(fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f), w4.w, alpha);
+                  alpha = fmaf(relu_nan(__uint_as_float(r[4 * j4 + 0])), w4.x, alpha);
+                  alpha = fmaf(relu_nan(__uint_as_float(r[4 * j4 + 1])), w4.y, alpha);
+                  alpha = fmaf(relu_nan(__uint_as_float(r[4 * j4 + 2])), w4.z, alpha);
+                  alpha = fmaf(relu_nan(__uint_as_float(r[4 * j4 + 3])), w4.w, alpha);
                 }
               }
             } else {
@@ -305,14 +305,14 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 w0 = wr4[(col >> 2) + j4], w1 = wr4[32 + (col >> 2) + j4], w2 = wr4[64 + (col >> 2) + j4];
-                const float v0 = fmaxf(__uint_as_float(r[4 * j4 + 0]), 0.f), v1 = fmaxf(__uint_as_float(r[4 * j4 + 1]), 0.f);
-                const float v2 = fmaxf(__uint_as_float(r[4 * j4 + 2]), 0.f), v3 = fmaxf(__uint_as_float(r[4 * j4 + 3]), 0.f);
+                const float v0 = relu_nan(__uint_as_float(r[4 * j4 + 0])), v1 = relu_nan(__uint_as_float(r[4 * j4 + 1]));
+                const float v2 = relu_nan(__uint_as_float(r[4 * j4 + 2])), v3 = relu_nan(__uint_as_float(r[4 * j4 + 3]));
                 c0 = fmaf(v0, w0.x, c0); c0 = fmaf(v1, w0.y, c0); c0 = fmaf(v2, w0.z, c0); c0 = fmaf(v3, w0.w, c0);
                 c1 = fmaf(v0, w1.x, c1); c1 = fmaf(v1, w1.y, c1); c1 = fmaf(v2, w1.z, c1); c1 = fmaf(v3, w1.w, c1);
                 c2 = fmaf(v0, w2.x, c2); c2 = fmaf(v1, w2.y, c2); c2 = fmaf(v2, w2.z, c2); c2 = fmaf(v3, w2.w, c2);
               }
               if (TRAIN) {
-                pack_chunk<true>(r, pw);
+                pack_chunk<true, false>(r, pw);
                 store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
                 *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd) * 4) = sign_bits(r);
               }

@@ -150,12 +150,15 @@ __device__ __forceinline__ uint32_t relu_mask_apply(uint32_t packed, uint32_t m)
 }
 __device__ __forceinline__ bool relu_mask_test(uint32_t m, int c) { return (m >> relu_mask_pos(c)) & 1u; }
 
-template <bool RELU>
+// SAT = true: clamp to the finite fp16 range (loss-scaled gradients of the backward chain); SAT = false: overflow to
+// inf so that the numerical guard sees it (forward activations, see pack_h2_ovf)
+template <bool RELU, bool SAT = true>
 __device__ __forceinline__ void pack_chunk(const uint32_t (&r)[32], uint32_t (&pw)[16]) {
 #pragma unroll
-  for (int w = 0; w < 16; ++w)
-    pw[w] = RELU ? pack_h2_relu(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]))
-                 : pack_h2(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]));
+  for (int w = 0; w < 16; ++w) {
+    const float lo = __uint_as_float(r[2 * w]), hi = __uint_as_float(r[2 * w + 1]);
+    pw[w] = RELU ? (SAT ? pack_h2_relu(lo, hi) : pack_h2_relu_ovf(lo, hi)) : (SAT ? pack_h2(lo, hi) : pack_h2_ovf(lo, hi));
+  }
 }
 // ---- stash blobs in global memory (activations / gradients kept for the wgrad GEMM) ----------------------
 // A [128 x C] fp16 blob is stored as two 64-row halves, each half in the tile-canonical layout with 64 rows:

@@ -91,7 +91,8 @@ __device__ __forceinline__ int motion_weight_offset(const lush_motion_net& net, 
 __global__ void __launch_bounds__(MOTION_THREADS)
 motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __restrict__ embed, int n_img,
                   const int64_t* __restrict__ idx, int64_t N, float* __restrict__ rows,
-                  float* __restrict__ out_r, float* __restrict__ out_v, float* __restrict__ out_ccw, int stage_w) {
+                  float* __restrict__ out_r, float* __restrict__ out_v, float* __restrict__ out_ccw, int stage_w,
+                  int* __restrict__ err_flag) {
   extern __shared__ float s_act[];                      // [MOTION_ROWS][rw]
   __shared__ int s_slot[MOTION_CHUNK];
   const int rw = net.row_width, C = net.embed_dim, M = net.num_motion;
@@ -155,8 +156,16 @@ motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __re
     const int cn = (int)min((int64_t)MOTION_CHUNK, N - n0);
     __syncthreads();
     for (int i = tid; i < cn; i += MOTION_THREADS) {
-      const int64_t r = idx[n0 + i] - row0;
-      s_slot[i] = (r >= 0 && r < nrows) ? (int)r : -1;
+      const int64_t img = idx[n0 + i], r = img - row0;
+      int slot = (r >= 0 && r < nrows) ? (int)r : -1;
+      // An image index outside [0, n_img) belongs to no CTA (the reference's nn.Embedding raises on it,
+      // models/lushnerf.py:32,119).  CTA 0 gives such a ray the identity kernel (r = v = 0, all weight on the original
+      // ray) so that its outputs are defined, and raises the caller's error flag.
+      if (blockIdx.x == 0 && (img < 0 || img >= n_img)) {
+        slot = -2;
+        if (err_flag) atomicOr(err_flag, LUSH_FLAG_BAD_IMAGE_INDEX);
+      }
+      s_slot[i] = slot;
     }
     __syncthreads();
 #pragma unroll 4
@@ -166,6 +175,9 @@ motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __re
       if (r >= 0) {
         out_r[n0 * nr + t] = s_act[r * rw + net.r_off + j];
         out_v[n0 * nr + t] = s_act[r * rw + net.v_off + j];
+      } else if (r == -2) {
+        out_r[n0 * nr + t] = 0.f;
+        out_v[n0 * nr + t] = 0.f;
       }
     }
 #pragma unroll 4
@@ -173,6 +185,7 @@ motion_fwd_kernel(const __grid_constant__ lush_motion_net net, const float* __re
       const int i = t / nc, j = t - i * nc;
       const int r = s_slot[i];
       if (r >= 0) out_ccw[n0 * nc + t] = s_act[r * rw + net.w_off + j];
+      else if (r == -2) out_ccw[n0 * nc + t] = j == 0 ? 1.f : 0.f;
     }
   }
 }
@@ -341,7 +354,7 @@ using namespace lush;
 
 extern "C" int lush_rbk_motion_fwd(const lush_motion_net* net, const float* embed, int n_img,
                                    const int64_t* images_idx, int64_t N, float* rows, float* r, float* v,
-                                   float* ccw, void* stream) {
+                                   float* ccw, int* err_flag, void* stream) {
   int rc = motion_check(net, "rbk_motion_fwd");
   if (rc) return rc;
   LUSH_REQUIRE(embed && n_img >= 1 && N >= 0 && rows && (N == 0 || (images_idx && r && v && ccw)),
@@ -358,7 +371,7 @@ extern "C" int lush_rbk_motion_fwd(const lush_motion_net* net, const float* embe
   }
   unsigned blocks = (unsigned)ceil_div(n_img, MOTION_ROWS);
   motion_fwd_kernel<<<blocks, MOTION_THREADS, smem, (cudaStream_t)stream>>>(*net, embed, n_img, images_idx, N, rows,
-                                                                            r, v, ccw, stage_w);
+                                                                            r, v, ccw, stage_w, err_flag);
   LUSH_LAUNCH_CHECK("rbk_motion_fwd");
   return 0;
 }

@@ -376,38 +376,53 @@ namespace lush {
 // Raw rays (o, d) of arbitrary (view, pixel) pairs, e.g. a training batch drawn on the device: replaces the
 // pre-expanded [V, H, W, ro+rd+rgb, 3] ray table and its host-side fancy indexing (reference run_lushnerf.py:538-616,
 // get_rays_np helpers:531-539).  rays [n, 3, 2] in the layout NeRFAll.forward takes.
-__global__ void ray_gen_gather_kernel(const float* __restrict__ poses, int pose_stride, const int64_t* __restrict__ view,
-                                      const int64_t* __restrict__ pix, PinholeConst cam, int W, int64_t n,
-                                      float* __restrict__ rays) {
+__global__ void ray_gen_gather_kernel(const float* __restrict__ poses, int n_views, int pose_stride, int row_stride,
+                                      const int64_t* __restrict__ view, const int64_t* __restrict__ pix,
+                                      PinholeConst cam, int W, int64_t npix, int64_t n, float* __restrict__ rays,
+                                      const float* __restrict__ images, float* __restrict__ rgb_out,
+                                      const uint8_t* __restrict__ masks, uint8_t* __restrict__ mask_out,
+                                      int* __restrict__ err_flag) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n) return;
-  const float* c2w = poses + view[t] * pose_stride;
-  const int64_t p = pix[t];
+  int64_t vi = view[t], p = pix[t];
+  int bad = 0;
+  if (vi < 0 || vi >= n_views) { bad |= LUSH_FLAG_BAD_VIEW_INDEX; vi = vi < 0 ? 0 : n_views - 1; }
+  if (p < 0 || p >= npix) { bad |= LUSH_FLAG_BAD_PIXEL_INDEX; p = p < 0 ? 0 : npix - 1; }
+  if (bad && err_flag) atomicOr(err_flag, bad);     // rare
+  const float* c2w = poses + vi * pose_stride;
   const int64_t j = p / W;
   const float fi = (float)(p - j * W), fj = (float)j;
   const float u = (fi + cam.ax) / cam.fx, v = -((fj + cam.ay) / cam.fy), w = -1.f;
   float* q = rays + t * 6;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    const float* row = c2w + r * 4;
+    const float* row = c2w + r * row_stride;
     q[2 * r] = row[3];
     q[2 * r + 1] = (u * row[0] + v * row[1]) + w * row[2];
   }
+  if (images) {
+    const float* src = images + (vi * npix + p) * 3;
+    rgb_out[t * 3 + 0] = src[0]; rgb_out[t * 3 + 1] = src[1]; rgb_out[t * 3 + 2] = src[2];
+  }
+  if (masks) mask_out[t] = masks[vi * npix + p];
 }
 }  // namespace lush
 
-extern "C" int lush_ray_gen_gather(const float* poses, int pose_stride, const int64_t* view_idx, const int64_t* pix_idx,
-                                   int H, int W, double fx, double fy, double cx, double cy, int64_t n, float* rays,
-                                   void* stream) {
-  LUSH_REQUIRE(poses && pose_stride >= 12 && H > 0 && W > 0 && fx != 0.0 && fy != 0.0 && n >= 0 &&
-                   (n == 0 || (view_idx && pix_idx && rays)),
+extern "C" int lush_ray_gen_gather(const float* poses, int n_views, int pose_stride, int pose_row_stride,
+                                   const int64_t* view_idx, const int64_t* pix_idx, int H, int W, double fx, double fy,
+                                   double cx, double cy, int64_t n, float* rays, const float* images, float* rgb_out,
+                                   const uint8_t* masks, uint8_t* mask_out, int* err_flag, void* stream) {
+  LUSH_REQUIRE(poses && n_views >= 1 && pose_row_stride >= 4 && pose_stride >= 2 * pose_row_stride + 4 && H > 0 &&
+                   W > 0 && fx != 0.0 && fy != 0.0 && n >= 0 && (n == 0 || (view_idx && pix_idx && rays)),
                "ray_gen_gather: bad arguments");
+  LUSH_REQUIRE((!images || rgb_out) && (!masks || mask_out), "ray_gen_gather: a table without its output buffer");
   if (n == 0) return 0;
   PinholeConst cam;
   cam.ax = (float)(0.5 - cx); cam.ay = (float)(0.5 - cy); cam.fx = (float)fx; cam.fy = (float)fy;
   int th = 256;
-  ray_gen_gather_kernel<<<(unsigned)ceil_div(n, th), th, 0, (cudaStream_t)stream>>>(poses, pose_stride, view_idx, pix_idx,
-                                                                                  cam, W, n, rays);
+  ray_gen_gather_kernel<<<(unsigned)ceil_div(n, th), th, 0, (cudaStream_t)stream>>>(
+      poses, n_views, pose_stride, pose_row_stride, view_idx, pix_idx, cam, W, (int64_t)H * W, n, rays, images, rgb_out,
+      masks, mask_out, err_flag);
   LUSH_LAUNCH_CHECK("ray_gen_gather");
   return 0;
 }

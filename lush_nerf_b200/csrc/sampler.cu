@@ -161,7 +161,8 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(float* __restrict__ keys,
 // smem per warp: cdf[S-1] + bins[S-1] + w[S-1] + z[S] + samples[PN] + out[S+N]
 __global__ void __launch_bounds__(kSamplerWarps * 32)
 sample_merge_kernel(const float* __restrict__ z, const float* __restrict__ weights,
-                    const float* __restrict__ u, int64_t u_stride, float* __restrict__ z_fine,
+                    const float* __restrict__ cdf_in, const float* __restrict__ u, int64_t u_stride,
+                    float* __restrict__ z_fine,
                     float* __restrict__ z_samples, float* __restrict__ z_std, int64_t R, int S, int N,
                     int PN, int per_warp) {
   extern __shared__ float smem[];
@@ -176,10 +177,14 @@ sample_merge_kernel(const float* __restrict__ z, const float* __restrict__ weigh
   float* s_smp = s_z + S;
   float* s_out = s_smp + PN;
   for (int j = lane; j < S; j += 32) s_z[j] = z[r * S + j];
-  for (int j = lane; j < S - 2; j += 32) s_w[j] = weights[r * S + j + 1];
+  if (cdf_in != nullptr) {      // strict mode: the caller's cdf [R, S-1] (e.g. the reference's torch.cumsum on this device)
+    for (int j = lane; j < nb; j += 32) s_cdf[j] = cdf_in[r * nb + j];
+  } else {
+    for (int j = lane; j < S - 2; j += 32) s_w[j] = weights[r * S + j + 1];
+  }
   __syncwarp();
   for (int j = lane; j < nb; j += 32) s_bins[j] = 0.5f * (s_z[j + 1] + s_z[j]);
-  warp_cdf_build(s_w, s_cdf, nb - 1, lane);
+  if (cdf_in == nullptr) warp_cdf_build(s_w, s_cdf, nb - 1, lane);
   __syncwarp();
   float sum = 0.f;
   for (int k = lane; k < N; k += 32) {
@@ -223,7 +228,11 @@ sample_merge_kernel(const float* __restrict__ z, const float* __restrict__ weigh
       }
     }
   }
-  // merge by rank
+  // merge by rank.  Precondition: z ascending and NaN-free (the stratified coarse samples are).  The output row is
+  // pre-filled with NaN so that a violated precondition (ranks collide, slots stay unwritten) is visible downstream
+  // -- the compositing kernel's NaN flag fires -- instead of leaking stale shared memory into z_fine.
+  for (int j = lane; j < S + N; j += 32) s_out[j] = __int_as_float(0x7fc00000);
+  __syncwarp();
   for (int i = lane; i < S; i += 32) {
     const float v = s_z[i];
     int lo = 0, hi = N;                       // #{samples < v}
@@ -266,10 +275,10 @@ extern "C" int lush_sample_pdf(const float* bins, const float* weights, const fl
   return 0;
 }
 
-extern "C" int lush_sample_merge(const float* z, const float* weights, const float* u,
+extern "C" int lush_sample_merge(const float* z, const float* weights, const float* cdf_in, const float* u,
                                  int64_t u_stride, float* z_fine, float* z_samples, float* z_std,
                                  int64_t R, int S, int N, void* stream) {
-  LUSH_REQUIRE(z && weights && u && z_fine && z_samples, "sample_merge: null pointer");
+  LUSH_REQUIRE(z && (weights || cdf_in) && u && z_fine && z_samples, "sample_merge: null pointer");
   LUSH_REQUIRE(R >= 0 && S >= 3 && N >= 1, "sample_merge: need S >= 3 and N >= 1");
   LUSH_REQUIRE(S + N <= 2048, "sample_merge: S+N > 2048 is not supported");
   if (R == 0) return 0;
@@ -284,8 +293,8 @@ extern "C" int lush_sample_merge(const float* z, const float* weights, const flo
     if (rc) return rc;
   }
   sample_merge_kernel<<<(unsigned)ceil_div(R, kSamplerWarps), kSamplerWarps * 32, smem,
-                        (cudaStream_t)stream>>>(z, weights, u, u_stride, z_fine, z_samples, z_std, R,
-                                                S, N, P, per_warp);
+                        (cudaStream_t)stream>>>(z, weights, cdf_in, u, u_stride, z_fine, z_samples,
+                                                z_std, R, S, N, P, per_warp);
   LUSH_LAUNCH_CHECK("sample_merge");
   return 0;
 }

@@ -214,6 +214,26 @@ __device__ __forceinline__ uint32_t pack_h2_relu(float lo, float hi) {
   asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// Overflowing variants (no saturation): a value beyond the fp16 range (|x| > 65504) becomes +-inf, NaN stays NaN.
+// The FORWARD activations use these: an fp16 overflow must not be clamped silently -- the inf / NaN it turns into
+// travels through the remaining layers into `raw`, where the compositing kernel's NaN/Inf flag word reports it
+// (the reference's "! [Numerical Error]" print, models/lushnerf.py:474-478).
+__device__ __forceinline__ uint32_t pack_h2_ovf(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_h2_relu_ovf(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// max(x, 0) that lets a NaN through (fmaxf would return 0 and hide an upstream overflow from the guard)
+__device__ __forceinline__ float relu_nan(float x) {
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // byte offset of element (r, c) inside a [rows x *] tile-canonical fp16 blob
 __host__ __device__ constexpr uint32_t blob_off(uint32_t rows, uint32_t r, uint32_t c) {

@@ -21,7 +21,6 @@ import time
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import ops
 from ..utils import rigid_warping
@@ -93,25 +92,6 @@ class Rigid_Blurring_Kernel(nn.Module):
         extras = {k: (blend(v) if torch.is_tensor(v) and 1 <= v.dim() <= 3 else v) for k, v in extras.items()}
         return rgb, depth, acc, extras
 
-    def _motion_mlp(self, e):
-        """e [rows, input_ch] -> (r, v, ccw) rows (reference :118-153)."""
-        h = e
-        for i, l in enumerate(self.view_embed_linears):
-            h = F.relu(l(h))
-            if i in self.skips:
-                h = torch.cat([e, h], -1)
-        hr, hv, hw = h, h, h
-        for l in self.r_branch:
-            hr = F.relu(l(hr))
-        for l in self.v_branch:
-            hv = F.relu(l(hv))
-        for l in self.w_branch:
-            hw = F.relu(l(hw))
-        r = self.r_linear(hr) * self.rv_window
-        v = self.v_linear(hv) * self.rv_window
-        w = torch.sigmoid(self.w_linear(hw))
-        return r, v, w / (torch.sum(w, dim=-1, keepdims=True) + 1e-10)
-
     def _motion_plan(self):
         """Layer program of the fused motion kernel, or None when the topology is outside what it covers."""
         table = getattr(self.view_embedding_layer, 'view_embed_layer', None)
@@ -155,13 +135,20 @@ class Rigid_Blurring_Kernel(nn.Module):
     def motion_params(self, rays_info):
         """(r, v, ccw) of every ray (reference :118-147).  The motion parameters are a function of the image
         index alone: the fused kernel evaluates the network once per IMAGE and the rays gather their image's row
-        (csrc/motion.cu).  `_motion_mlp` is the same computation with torch ops on the gathered embeddings; it
-        is what the kernel is tested against and what runs for a topology the kernel does not cover."""
+        (csrc/motion.cu).  There is no eager path: a topology the kernel's layer program cannot express raises.
+        (tests/test_kernels_gpu.py::motion_mlp_torch is the same computation with torch ops on gathered embeddings:
+        the definition the kernel is tested against.)"""
         idx = rays_info['images_idx'].squeeze(-1)
-        plan = self._motion_plan() if idx.is_cuda and os.environ.get("LUSH_FUSED_MOTION", "1") != "0" else None
-        if plan is not None:
-            return ops.rbk_motion(idx, plan, self.view_embedding_layer.view_embed_layer.weight, plan.params)
-        return self._motion_mlp(self.view_embedding_layer(idx))
+        if not idx.is_cuda:
+            raise RuntimeError("lush_nerf_b200 blur kernel needs CUDA tensors; there is no CPU fallback")
+        plan = self._motion_plan()
+        if plan is None:
+            raise NotImplementedError("Rigid_Blurring_Kernel: this topology is outside the fused motion kernel (at most "
+                                      f"{ops._lib.MOTION_MAX_LAYERS} layers, an nn.Embedding table without max_norm, an "
+                                      "activation row that fits shared memory)")
+        # err_flags: the owning NeRFAll's guard word (set by NeRFAll.forward); None -> indices validated on the host
+        return ops.rbk_motion(idx, plan, self.view_embedding_layer.view_embed_layer.weight, plan.params,
+                              self.__dict__.get('err_flags'))
 
     def forward(self, rays, rays_info):
         r, v, w = self.motion_params(rays_info)
@@ -229,13 +216,16 @@ class NeRFAll(nn.Module):
         return self._flags
 
     def _guard_report(self, device, tag=""):
+        """LUSH_NUMERIC_GUARD = lazy (default: the flag word of call i is read when call i+1 finds its copy complete, no
+        host sync) | sync | off.  Nothing is queried or copied while the stream is being captured into a CUDA graph; a
+        captured training step is checked by Trainer.step every `guard_every` replays instead."""
         mode = os.environ.get("LUSH_NUMERIC_GUARD", "lazy")
-        if mode == "off" or self._flags is None:
+        if mode == "off" or self._flags is None or torch.cuda.is_current_stream_capturing():
             return
         if self._flags_pending is not None and (mode == "sync" or self._flags_pending[1].query()):
             host, ev = self._flags_pending
             ev.synchronize()
-            self._print_flags(int(host.item()))
+            self._print_flags(int(host.item()), self._overflow_hint())
             self._flags_pending = None
         if self._flags_pending is None:
             host = torch.empty(1, dtype=torch.int32, pin_memory=True)
@@ -246,16 +236,33 @@ class NeRFAll(nn.Module):
             self._flags_pending = (host, ev)
             if mode == "sync":
                 ev.synchronize()
-                self._print_flags(int(host.item()))
+                self._print_flags(int(host.item()), self._overflow_hint())
                 self._flags_pending = None
 
+    def _overflow_hint(self):
+        """The fp16-operand tensor-core path overflows where fp32 would not: activations beyond 65504 become inf (they
+        are NOT clamped) and reach `raw` as inf / NaN, which is what this guard then reports."""
+        nets = [n for n in (self.mlp_coarse, self.mlp_fine) if n is not None]
+        if any(n.impl() == 1 for n in nets):
+            return (" (tcgen05 MLP path: fp16 operands overflow beyond |x| = 65504; LUSH_MLP_IMPL=simt or "
+                    "net.mlp_impl = 0 selects the exact-fp32 kernels)")
+        return ""
+
     @staticmethod
-    def _print_flags(bits):
+    def _print_flags(bits, hint=""):
+        from .._lib import FLAG_BAD_IMAGE_INDEX, FLAG_BAD_PIXEL_INDEX, FLAG_BAD_VIEW_INDEX
+        if bits & (FLAG_BAD_IMAGE_INDEX | FLAG_BAD_VIEW_INDEX | FLAG_BAD_PIXEL_INDEX):
+            what = [n for n, b in (("rays_info['images_idx']", FLAG_BAD_IMAGE_INDEX), ("view index", FLAG_BAD_VIEW_INDEX),
+                                   ("pixel index", FLAG_BAD_PIXEL_INDEX)) if bits & b]
+            # the reference raises here (nn.Embedding / fancy indexing); the kernels clamped the offending rays and
+            # set a flag, which surfaces one call later (lazy guard) or at once (LUSH_NUMERIC_GUARD=sync)
+            raise IndexError(f"index out of range in a previous kernel call: {', '.join(what)}")
         for key, sh in _GUARD_KEYS:
+            extra = hint if key == "raw" else ""
             if bits >> sh & 1:
-                print(f"! [Numerical Error] {key} contains nan.")
+                print(f"! [Numerical Error] {key} contains nan.{extra}")
             if bits >> sh & 2:
-                print(f"! [Numerical Error] {key} contains inf.")
+                print(f"! [Numerical Error] {key} contains inf.{extra}")
 
     def _draw(self, kind, shape, device):
         if self.rng_override is not None:
@@ -451,6 +458,7 @@ class NeRFAll(nn.Module):
             if use_rbk:
                 if not self.blur_kernel_net.use_dpnerf:
                     return None  # the reference falls through without a return here too
+                self.mlp_rbk.__dict__['err_flags'] = self._guard_flags(rays.device)   # bad images_idx -> flag bit 10
                 rays_transform, ccw = self.mlp_rbk(rays, rays_info)
                 Kr = ccw.shape[-1]
                 if allkernel:

@@ -82,24 +82,54 @@ def ray_gen_prep(c2w: torch.Tensor, H: int, W: int, K, near=0.0, far=1.0, ndc=Tr
     return out
 
 
-def ray_gen_gather(poses: torch.Tensor, view_idx: torch.Tensor, pix_idx: torch.Tensor, H: int, W: int, K):
-    """rays [n, 3, 2] of the (view, pixel) pairs: a training batch's rays generated on the device from the poses
-    ([V,3,4] or [V,4,4]) instead of looked up in a pre-expanded ray table (no gradient: poses are constants)."""
+def ray_gen_gather(poses: torch.Tensor, view_idx: torch.Tensor, pix_idx: torch.Tensor, H: int, W: int, K,
+                   images: Optional[torch.Tensor] = None, masks: Optional[torch.Tensor] = None,
+                   err_flags: Optional[torch.Tensor] = None, validate: bool = False):
+    """A training batch staged on the device.  rays [n, 3, 2] of the (view, pixel) pairs generated from the poses
+    ([V,3,4], [V,4,4] or the LLFF [V,3,5] block) instead of looked up in a pre-expanded ray table; with `images`
+    ([V,H,W,3] fp32) and / or `masks` ([V,H,W] bool / uint8) the pixels' target colours and mask bits come back too:
+    returns rays, or (rays, rgb, mask) when a table is given (None for the missing one).  No gradient (constants).
+    An index outside its range is clamped and flagged in `err_flags` (int32[1], e.g. the model's guard word);
+    validate=True reads the flag back (one host sync) and raises IndexError like the reference's fancy indexing would."""
     if not poses.is_cuda:
         raise RuntimeError("lush_nerf_b200.ray_gen_gather needs CUDA tensors; there is no CPU fallback")
     poses = _f32c(poses.detach())
-    if poses.dim() != 3 or poses.shape[1] < 3 or poses.shape[2] != 4:
-        raise ValueError(f"ray_gen_gather: poses must be [V,3,4] or [V,4,4], got {tuple(poses.shape)}")
+    if poses.dim() != 3 or poses.shape[1] < 3 or poses.shape[2] < 4:
+        raise ValueError(f"ray_gen_gather: poses must be [V,3,4], [V,4,4] or [V,3,5], got {tuple(poses.shape)}")
     view_idx, pix_idx = view_idx.reshape(-1).contiguous(), pix_idx.reshape(-1).contiguous()
     if view_idx.numel() != pix_idx.numel():
         raise ValueError("ray_gen_gather: view_idx and pix_idx differ in length")
-    n = view_idx.numel()
+    n, V = view_idx.numel(), poses.shape[0]
     out = _empty((n, 3, 2), poses)
-    check(lib().lush_ray_gen_gather(ptr(poses, "poses"), poses.shape[1] * 4, ptr(view_idx, "view_idx", torch.int64),
-                                    ptr(pix_idx, "pix_idx", torch.int64), int(H), int(W), float(K[0][0]),
-                                    float(K[1][1]), float(K[0][2]), float(K[1][2]), n, ptr(out), stream()),
-          "lush_ray_gen_gather")
-    return out
+    rgb = mask = None
+    if images is not None:
+        images = _f32c(images)
+        if images.numel() != V * H * W * 3:
+            raise ValueError(f"ray_gen_gather: images must hold [V={V}, {H}, {W}, 3] floats, got {tuple(images.shape)}")
+        rgb = _empty((n, 3), poses)
+    if masks is not None:
+        masks = masks.contiguous()
+        masks = masks.view(torch.uint8) if masks.dtype == torch.bool else masks
+        if masks.dtype != torch.uint8 or masks.numel() != V * H * W:
+            raise ValueError(f"ray_gen_gather: masks must be [V={V}, {H}, {W}] bool / uint8")
+        mask = torch.empty(n, dtype=torch.uint8, device=poses.device)
+    if validate and err_flags is None:
+        err_flags = torch.zeros(1, dtype=torch.int32, device=poses.device)
+    check(lib().lush_ray_gen_gather(
+        ptr(poses, "poses"), V, poses.shape[1] * poses.shape[2], poses.shape[2], ptr(view_idx, "view_idx", torch.int64),
+        ptr(pix_idx, "pix_idx", torch.int64), int(H), int(W), float(K[0][0]), float(K[1][1]), float(K[0][2]),
+        float(K[1][2]), n, ptr(out), ptr(images, "images"), ptr(rgb), ptr(masks, "masks", torch.uint8),
+        ptr(mask, "mask_out", torch.uint8), ptr(err_flags, "err_flags", torch.int32), stream()), "lush_ray_gen_gather")
+    if validate:
+        bits = int(err_flags.item())
+        if bits & (_lib.FLAG_BAD_VIEW_INDEX | _lib.FLAG_BAD_PIXEL_INDEX):
+            err_flags.bitwise_and_(~(_lib.FLAG_BAD_VIEW_INDEX | _lib.FLAG_BAD_PIXEL_INDEX))
+            what = " and ".join(w for w, b in (("view index", _lib.FLAG_BAD_VIEW_INDEX), ("pixel index", _lib.FLAG_BAD_PIXEL_INDEX))
+                                if bits & b)
+            raise IndexError(f"ray_gen_gather: {what} out of range (V={V}, H*W={H * W})")
+    if images is None and masks is None:
+        return out
+    return out, rgb, (mask.view(torch.bool) if mask is not None else None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -180,6 +210,32 @@ def composite(raw, z, rays_d, sigma_noise=None, rm_near_thresh: float = -1.0, wh
 # ------------------------------------------------------------------------------------------------
 # hierarchical sampling (reference helpers:566-609; models/lushnerf.py:435-440,465)
 # ------------------------------------------------------------------------------------------------
+def sample_strict(det: bool) -> bool:
+    """Which cdf feeds the search kernel.  LUSH_SAMPLE_STRICT = det (default) | 1 | 0:
+      strict -> the cdf is built by the reference's own op sequence (helpers:568-571: + 1e-5, / sum, torch.cumsum, cat)
+                with torch ops ON THIS DEVICE, the kernel only searches / gathers / interpolates: indices and samples
+                equal what the reference's searchsorted produces on the same GPU, bit for bit;
+      fused  -> the cdf is built inside the kernel in a fixed warp-scan order (no extra launches); cdf entries move by
+                <= 4 ulp against torch's order, which can flip an index only where u touches a cdf entry.
+    Default: strict for deterministic sampling (rendering, perturb = 0: where 'bit-exact indices' is defined), fused for
+    random u (training: the draw itself differs from run to run)."""
+    mode = os.environ.get("LUSH_SAMPLE_STRICT", "det").lower()
+    if mode in ("1", "true", "always", "on"):
+        return True
+    if mode in ("0", "false", "never", "off"):
+        return False
+    return bool(det)
+
+
+@torch.no_grad()
+def reference_cdf(weights: torch.Tensor) -> torch.Tensor:
+    """cdf [R, nb] of weights [R, nb-1], op for op as the reference builds it (helpers:568-571)."""
+    w = weights + 1e-5
+    pdf = w / torch.sum(w, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    return torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1).contiguous()
+
+
 @torch.no_grad()
 def sample_pdf_cuda(bins, weights, u, cdf: Optional[torch.Tensor] = None, return_inds=False):
     bins, weights, u = _f32c(bins), _f32c(weights), _f32c(u)
@@ -195,16 +251,19 @@ def sample_pdf_cuda(bins, weights, u, cdf: Optional[torch.Tensor] = None, return
 
 
 @torch.no_grad()
-def sample_merge(z, weights, u, want_std=True):
-    """Fused z_mid + sample_pdf(weights[:,1:-1]) + sort(cat(z, samples)) + z_std."""
+def sample_merge(z, weights, u, want_std=True, strict: Optional[bool] = None):
+    """Fused z_mid + sample_pdf(weights[:,1:-1]) + sort(cat(z, samples)) + z_std.  z must be ascending per row (the
+    merge is by rank).  strict: see sample_strict(); None -> strict iff u is the shared deterministic [N] vector."""
     z, weights, u = _f32c(z), _f32c(weights), _f32c(u)
     R, S = z.shape
     N = u.shape[-1]
     u_stride = 0 if u.dim() == 1 else N
+    strict = sample_strict(u.dim() == 1) if strict is None else strict
+    cdf = reference_cdf(weights[:, 1:-1]) if strict else None
     z_fine, z_samples = _empty((R, S + N), z), _empty((R, N), z)
     z_std = _empty((R,), z) if want_std else None
-    check(lib().lush_sample_merge(ptr(z, "z"), ptr(weights, "weights"), ptr(u, "u"), u_stride, ptr(z_fine),
-                                  ptr(z_samples), ptr(z_std), R, S, N, stream()), "lush_sample_merge")
+    check(lib().lush_sample_merge(ptr(z, "z"), ptr(weights, "weights"), ptr(cdf, "cdf"), ptr(u, "u"), u_stride,
+                                  ptr(z_fine), ptr(z_samples), ptr(z_std), R, S, N, stream()), "lush_sample_merge")
     return z_fine, z_samples, z_std
 
 
@@ -213,6 +272,15 @@ def sample_merge(z, weights, u, want_std=True):
 # ------------------------------------------------------------------------------------------------
 # bench.py sets this to a list to collect (start, end) CUDA-event pairs around every MLP launch sequence
 MLP_EVENT_SINK = None
+# train.ArenaGradAllReduce sets this to `fn(flat_grad_tensor)`: called from inside backward as soon as the kernels that
+# fill a network's flat gradient arena are enqueued, so the arena's all-reduce can start while the rest of the
+# backward pass (the other network) is still running
+GRAD_ARENA_HOOK = None
+
+
+def _arena_done(g_flat):
+    if GRAD_ARENA_HOOK is not None:
+        GRAD_ARENA_HOOK(g_flat)
 
 
 class _Timed:
@@ -280,6 +348,7 @@ class _MLP(torch.autograd.Function):
         with _Timed("bwd" if impl == 1 else "bwd_simt"):
             check(L.lush_mlp_bwd(byref(desc), ptr(flat), ptr(rb), rb.shape[1], ptr(z), ptr(g_out), ptr(stash),
                                  ptr(g_flat), ptr(g_rb), ptr(ws), wb, R, S, impl, stream()), "lush_mlp_bwd")
+        _arena_done(g_flat)
         grads, off = [], 0
         for n, shp, need in zip(numels, shapes, ctx.needs_input_grad[6:]):
             grads.append(g_flat[off:off + n].view(shp) if need else None)
@@ -376,7 +445,7 @@ class MotionPlan:
 
 class _RbkMotion(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, idx, plan, embed, *params):
+    def forward(ctx, idx, plan, err_flags, embed, *params):
         idx = idx.reshape(-1).contiguous()
         embed = _f32c(embed)
         params = [_f32c(p) for p in params]
@@ -385,7 +454,8 @@ class _RbkMotion(torch.autograd.Function):
         r, v, ccw = _empty((N, 3 * M), embed), _empty((N, 3 * M), embed), _empty((N, M + 1), embed)
         net = plan.net(params)
         check(lib().lush_rbk_motion_fwd(byref(net), ptr(embed, "embedding"), n_img, ptr(idx, "images_idx", torch.int64),
-                                        N, ptr(rows), ptr(r), ptr(v), ptr(ccw), stream()), "lush_rbk_motion_fwd")
+                                        N, ptr(rows), ptr(r), ptr(v), ptr(ccw),
+                                        ptr(err_flags, "err_flags", torch.int32), stream()), "lush_rbk_motion_fwd")
         ctx.save_for_backward(idx, rows, embed, *params)
         ctx.plan = plan
         ctx.set_materialize_grads(False)
@@ -406,16 +476,24 @@ class _RbkMotion(torch.autograd.Function):
         check(lib().lush_rbk_motion_bwd(byref(net), embed.shape[0], ptr(idx, "images_idx", torch.int64), idx.numel(),
                                         ptr(rows), ptr(_f32c(g_r)), ptr(_f32c(g_v)), ptr(_f32c(g_ccw)),
                                         ptr(g_embed), stream()), "lush_rbk_motion_bwd")
+        _arena_done(flat)
         need = ctx.needs_input_grad
-        return (None, None, g_embed if need[2] else None,
-                *[g if nd else None for g, nd in zip(grads, need[3:])])
+        return (None, None, None, g_embed if need[3] else None,
+                *[g if nd else None for g, nd in zip(grads, need[4:])])
 
 
-def rbk_motion(images_idx, plan: MotionPlan, embed_weight, params):
-    """(r [N,3M], v [N,3M], ccw [N,M+1]) for the rays' image indices; one kernel forward, one backward."""
+def rbk_motion(images_idx, plan: MotionPlan, embed_weight, params, err_flags: Optional[torch.Tensor] = None):
+    """(r [N,3M], v [N,3M], ccw [N,M+1]) for the rays' image indices; one kernel forward, one backward.
+    An index outside [0, num_img) -- nn.Embedding raises on it in the reference -- gives that ray the identity
+    kernel and sets LUSH_FLAG_BAD_IMAGE_INDEX in `err_flags` (int32[1]); without `err_flags` the indices are
+    validated here with one host sync (IndexError)."""
     if not embed_weight.is_cuda:
         raise RuntimeError("lush_nerf_b200.rbk_motion needs CUDA tensors; there is no CPU fallback")
-    return _RbkMotion.apply(images_idx, plan, embed_weight, *params)
+    if err_flags is None and images_idx.numel() and not torch.cuda.is_current_stream_capturing():
+        lo, hi = int(images_idx.min()), int(images_idx.max())
+        if lo < 0 or hi >= embed_weight.shape[0]:
+            raise IndexError(f"rbk_motion: images_idx in [{lo}, {hi}] outside the embedding table [0, {embed_weight.shape[0]})")
+    return _RbkMotion.apply(images_idx, plan, err_flags, embed_weight, *params)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -6,6 +6,8 @@ reference keeps in this file (frequency masks, visualisation, MS-SSIM) is out of
 """
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -14,6 +16,7 @@ from .. import ops
 from .._lib import MlpDesc
 
 HALF_PIX = 0.5
+_FALLBACK_WARNED = set()
 
 # ---- small host-side metrics the driver star-imports (reference helpers:9-12)
 img2mse = lambda x, y: torch.mean((x - y) ** 2)
@@ -126,10 +129,21 @@ class _FlatParamMLP(nn.Module):
         return self._desc
 
     def impl(self, training: bool = False) -> int:
-        """1 = tcgen05 fp16-operand kernels when they cover this topology (and this mode), else 0 = fp32 SIMT."""
+        """1 = tcgen05 fp16-operand kernels when they cover this topology (and this mode), else 0 = fp32 SIMT.
+        A scene network the tensor-core kernels do not cover (width != 256, ...) runs on the ~50x slower exact-fp32
+        SIMT kernels: that is announced once per topology instead of happening silently."""
         want = getattr(self, "mlp_impl", None)
         want = ops.default_mlp_impl() if want is None else want
-        return want if ops.mlp_impl_supported(self._desc, want, training) else 0
+        if ops.mlp_impl_supported(self._desc, want, training):
+            return want
+        if want == 1 and self.out_mode == 0:
+            key = (self.D, self.W, self.input_ch, self.input_ch_views, tuple(self.skips), bool(training))
+            if key not in _FALLBACK_WARNED:
+                _FALLBACK_WARNED.add(key)
+                warnings.warn(f"lush_nerf_b200: the tcgen05 MLP kernels do not cover this topology (D={self.D}, "
+                              f"W={self.W}, skips={self.skips}, training={bool(training)}); it runs on the exact-fp32 "
+                              "SIMT kernels (~20 TFLOP/s instead of ~1000)", RuntimeWarning, stacklevel=3)
+        return 0
 
     def render(self, ray_batch, z):
         """Fused encode+MLP on the samples x = o + d*z of each ray -> [R, S, C]."""
@@ -138,20 +152,19 @@ class _FlatParamMLP(nn.Module):
         return ops.mlp_apply(ray_batch, z, self._desc, self.impl(training), self.flat_params(), ps)
 
     def forward(self, x, force_naive=True, inference=False):
-        """Reference call surface: x = [embedded pts | embedded views] (helpers:394).  The fused kernels
-        consume rays, not embeddings, so this compatibility entry evaluates the same topology with
-        torch ops; NeRFAll never calls it."""
-        import torch.nn.functional as F
-        e_pts, e_views = torch.split(x, [self.input_ch, self.input_ch_views], dim=-1)
-        h = e_pts
-        for i, l in enumerate(self.pts_linears):
-            h = F.relu(l(h))
-            if i in self.skips:
-                h = torch.cat([e_pts, h], -1)
-        alpha = self.alpha_linear(h)
-        hv = F.relu(self.views_linears[0](torch.cat([self.feature_linear(h), e_views], -1)))
-        rgb = self.rgb_linear(hv)
-        return torch.cat([rgb, alpha], -1) if self.out_mode == 0 else rgb
+        """Reference call surface (helpers:394 / :483): x = [gamma(p) | gamma(d)] -> [M, 4] (NeRF) or [M, 3]
+        (NeRF_Noise).  The fused kernels consume points, not encodings, and gamma() carries its argument in its first
+        three columns (include_input=True, helpers:325-326): p = x[:, 0:3], d = x[:, in_ch:in_ch+3] are read back and
+        the points go through the same fused encode+MLP kernels as everything else.  x must therefore BE the encoding
+        of those columns -- the only way the reference ever calls a network (models/lushnerf.py:238-257)."""
+        if x.shape[-1] != self.input_ch + self.input_ch_views:
+            raise ValueError(f"expected {self.input_ch + self.input_ch_views} input channels, got {x.shape[-1]}")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        pts, dirs = x2[:, 0:3], x2[:, self.input_ch:self.input_ch + 3]
+        rb = torch.cat([pts, torch.zeros_like(pts), torch.zeros_like(pts[:, :2]), dirs], -1)
+        out = self.render(rb, torch.zeros_like(pts[:, :1]))
+        return out.reshape(*lead, out.shape[-1])
 
 
 class NeRF(_FlatParamMLP):
@@ -226,7 +239,9 @@ def ndc_rays(H, W, focal, near, rays_o, rays_d):
 def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
     """Same signature and random-number consumption as the reference: det -> u = linspace(0,1,N),
     else one torch.rand([..., N]); pytest -> numpy seed 0.  Search / gather / lerp run in the warp-level
-    kernel (csrc/sampler.cu)."""
+    kernel (csrc/sampler.cu).  det=True (and LUSH_SAMPLE_STRICT=1) feed the kernel the cdf built by the reference's
+    own torch ops on this device (ops.reference_cdf): indices and samples are then bit-identical to the reference's
+    searchsorted path on the same GPU; otherwise the cdf is built inside the kernel (ops.sample_strict)."""
     lead = list(bins.shape[:-1])
     b2 = bins.reshape(-1, bins.shape[-1])
     w2 = weights.reshape(-1, weights.shape[-1])
@@ -241,7 +256,8 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
         u = ops.linspace01(N_samples, bins.device)
     else:
         u = torch.rand(lead + [N_samples], device=bins.device).reshape(-1, N_samples)
-    return ops.sample_pdf_cuda(b2, w2, u).reshape(lead + [N_samples])
+    cdf = ops.reference_cdf(w2) if ops.sample_strict(det) else None
+    return ops.sample_pdf_cuda(b2, w2, u, cdf=cdf).reshape(lead + [N_samples])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,7 +279,37 @@ def smart_load_state_dict(model: nn.Module, state_dict: dict):
     model.load_state_dict(sd, strict=False)
 
 
-def compute_mean_with_confidence(A, certainty, threshold):
+# ------------------------------------------------------------------------------------------------
+# frequency masks (reference helpers:630-662): host-side, once per run -- which pixels receive blur-kernel ray
+# gradients in stage 2 (run_lushnerf.py:283, :627-628).  numpy FFT instead of the reference's cv2.dft.
+# ------------------------------------------------------------------------------------------------
+def frequency_mask(image, radius=50):
+    """image [H,W,3] uint8 -> [H,W] {0,1}: centred low-pass window of +-radius frequencies, magnitude of the filtered
+    image normalised to 0..255 and thresholded at 48."""
+    img = np.asarray(image)
+    gray = (0.299 * img[..., 0].astype(np.float64) + 0.587 * img[..., 1] + 0.114 * img[..., 2])
+    if img.dtype == np.uint8:
+        gray = np.floor(gray + 0.5)            # cv2.cvtColor rounds to uint8 before the float conversion
+    spec = np.fft.fftshift(np.fft.fft2(gray.astype(np.float32)))
+    rows, cols = gray.shape
+    crow, ccol = rows // 2, cols // 2
+    keep = np.zeros((rows, cols), bool)
+    keep[crow - radius:crow + radius, ccol - radius:ccol + radius] = True     # (a negative start wraps, as upstream)
+    low = np.abs(np.fft.ifft2(np.fft.ifftshift(spec * keep)))     # cv2.idft is unscaled; the normalisation below removes it
+    span = low.max() - low.min()
+    low = (low - low.min()) / (span if span > 0 else 1.0) * 255
+    return (low > 48).astype(np.float32)
+
+
+def get_masks_for_images(images, radius=50):
+    """images [V,H,W,3] uint8 -> masks [V,H,W] uint8."""
+    masks = np.zeros(images.shape[:-1], dtype=np.uint8)
+    for i, image in enumerate(images):
+        masks[i] = frequency_mask(image, radius)
+    return masks
+
+
+def compute_mean_with_confidence(A, certainty, threshold=0.2):
     """Confidence-masked mean over views (reference helpers:665-688): A [V,P,3], certainty [V,P]."""
     mask = (certainty >= threshold).unsqueeze(-1).to(A.dtype)
     total = (A * mask).sum(0)

@@ -45,7 +45,7 @@ def test_header_symbols_all_exported():
     for name in sorted(declared):
         assert hasattr(handle, name), f"{name} declared in the header but not exported"
     assert set(_lib.exported_symbols()) == declared
-    assert _lib.lib().lush_abi_version() == 1
+    assert _lib.lib().lush_abi_version() == 2
 
 
 def test_argument_validation_without_gpu():

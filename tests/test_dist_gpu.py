@@ -1,0 +1,125 @@
+"""GPU, 2 ranks over NCCL (skipped on a 1-GPU box): the ray-sharded training step of lush_nerf_b200.train.Trainer
+-- every rank renders its half of the global batch, the gradient arenas are all-reduced (AVG) in place from inside the
+backward pass -- must reproduce the 1-rank step on the whole batch.  Random draws are generated for the GLOBAL batch
+and sliced per rank, so the two runs see the same numbers.
+
+Tolerances: exact-fp32 MLP path 2e-5 relative L2 per tensor (fp32 atomics, summation order); tcgen05 path 1e-2 (each
+shard picks its own power-of-two loss scale for the fp16 gradient chain)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+NPX, S, N, KR = 64, 24, 16, 5
+H, W, F = 40, 60, 50.0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _inputs():
+    from oracle import lush_oracle as O
+    g = torch.Generator().manual_seed(21)
+    K = np.array([[F, 0, 0.5 * W], [0, F, 0.5 * H], [0, 0, 1]])
+    c2w = torch.tensor([[0.99, 0.02, -0.1, 0.1], [-0.02, 0.999, 0.03, -0.05], [0.1, -0.03, 0.99, 0.2]])
+    ro, rd = O.get_rays(H, W, K, c2w)
+    rays = torch.stack([ro, rd], -1).reshape(-1, 3, 2)[torch.randperm(H * W, generator=g)[:NPX]].contiguous()
+    R = NPX * KR
+    draws = [torch.rand(R, S, generator=g), torch.randn(R, S - 1, generator=g), torch.rand(R, N, generator=g),
+             torch.randn(R, S + N - 1, generator=g)]
+    batch = dict(rays=rays, rgbsf=torch.rand(NPX, 3, generator=g), fq_mask=torch.rand(NPX, generator=g) < 0.5,
+                 images_idx=torch.randint(0, 20, (NPX, 1), generator=g))
+    return K, batch, draws
+
+
+def _trainer(dev, impl, K):
+    from lush_nerf_b200.synthetic import build_model, poster_args
+    from lush_nerf_b200.train import Trainer
+    from oracle import lush_oracle as O
+    nets, rbk = O.det_nets(O.POSTER_CFG, tag=1, sigma_gain=30.0), O.det_rbk_params(tag=7)
+    m = build_model(poster_args(N_samples=S, N_importance=N))
+    m.load_state_dict(O.reference_state_dict(nets, rbk), strict=False)
+    m = m.to(dev).train()
+    for net in (m.mlp_coarse, m.mlp_fine):
+        net.mlp_impl = impl
+    rk = dict(perturb=1.0, N_importance=N, N_samples=S, use_viewdirs=True, white_bkgd=False, raw_noise_std=1.0,
+              inference=False, near=0.0, far=1.0)
+    return Trainer(m, H, W, K, lrate=5e-4, render_kwargs=rk)
+
+
+def _grads_of_step(tr, batch, draws, lo, hi, dev):
+    from tests.test_model_gpu import inject
+    inject(tr.model, [d[lo * KR:hi * KR] for d in draws])
+    b = {k: v[lo:hi].to(dev) for k, v in batch.items()}
+    loss = tr._fwd_bwd(b)
+    tr.allreduce.finish()
+    torch.cuda.synchronize(dev)
+    return float(loss), {n: p.grad.detach().cpu().numpy().copy() for n, p in tr.model.named_parameters() if p.grad is not None}
+
+
+def _worker(rank, world, port, impl, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from lush_nerf_b200.train import shard_rows
+        K, batch, draws = _inputs()
+        tr = _trainer(dev, impl, K)
+        lo, hi = shard_rows(NPX, rank, world)
+        loss, grads = _grads_of_step(tr, batch, draws, lo, hi, dev)
+        assert tr.allreduce.arenas and len(tr.allreduce.arenas) >= 4      # coarse, fine, noise, blur-kernel network
+        q.put((rank, loss, grads))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("impl,tol", [(0, 2e-5), (1, 1e-2)])
+def test_two_rank_sharded_step_equals_one_rank_step(impl, tol):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, impl, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        got = {}
+        for _ in range(world):
+            rank, loss, grads = q.get(timeout=600)
+            got[rank] = (loss, grads)
+    finally:
+        for p in procs:
+            p.join(timeout=120)
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs)
+    K, batch, draws = _inputs()
+    dev = torch.device("cuda", 0)
+    tr = _trainer(dev, impl, K)
+    loss1, ref = _grads_of_step(tr, batch, draws, 0, NPX, dev)
+    assert abs(0.5 * (got[0][0] + got[1][0]) - loss1) <= 1e-5 * max(1.0, abs(loss1)) + (0 if impl == 0 else 1e-4)
+    assert set(got[0][1]) == set(got[1][1]) == set(ref)
+    worst = 0.0
+    for n in ref:
+        a, b = got[0][1][n], got[1][1][n]
+        assert np.array_equal(a, b), f"{n}: the two ranks hold different reduced gradients"
+        r = ref[n].astype(np.float64)
+        if np.linalg.norm(r) < 1e-12:
+            assert np.abs(a).max() < 1e-9, n
+            continue
+        rel = np.linalg.norm(a - r) / np.linalg.norm(r)
+        worst = max(worst, rel)
+        assert rel <= tol, (n, rel)
+    print(f"2-rank vs 1-rank gradients (impl={impl}): worst rel-L2 {worst:.2e}")

@@ -21,6 +21,12 @@ COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-st
           "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 if os.environ.get("LUSH_CHAIN_TRACE", "0") not in ("", "0"):
     COMMON.append("-DLUSH_CHAIN_TRACE")      # timeline probes of the chain kernels (tools/trace_chain.py); use --force
+# experiment builds (tools/jobs/*): LUSH_BUILD_DEFINES="-DLUSH_EXP_NO_STASH ..." LUSH_BUILD_OUT=lib_exp.so python -m lush_nerf_b200.build
+if os.environ.get("LUSH_BUILD_DEFINES"):
+    COMMON += os.environ["LUSH_BUILD_DEFINES"].split()
+if os.environ.get("LUSH_BUILD_OUT"):
+    LIB = os.path.abspath(os.environ["LUSH_BUILD_OUT"])
+    OBJ = OBJ + "_" + os.path.splitext(os.path.basename(LIB))[0]
 # per-file extra flags: the scan / sampler / ray kernels follow the reference's unfused fp32 op
 # sequence (bit-exact sample_pdf indices), so FMA contraction is disabled there.
 EXTRA = {

@@ -12,6 +12,12 @@ namespace lush {
 
 constexpr int kWarpsPerBlock = 8;
 
+// Colour activation.  1 / (1 + exp(-x)) with the hardware exp2 / reciprocal units (ex2.approx, rcp.approx: <= 2 ulp each):
+// |error| <= 3e-7 on a value in [0, 1], against <= 1e-7 for the exact expf + correctly rounded reciprocal it replaces
+// -- one third of the instructions of these issue-bound kernels.  The transmittance path (exp(-sigma dist), products)
+// stays exact: its errors would be amplified by the 1 - exp() cancellation.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
 struct RayChunk {
   float4 rw;     // raw sample
   float z, zn;   // z_i, z_{i+1}
@@ -50,18 +56,36 @@ __device__ __forceinline__ SampleFwd sample_fwd(const RayChunk& c, bool has_next
   return f;
 }
 
-__device__ __forceinline__ void load_chunk(RayChunk& c, const float* __restrict__ raw,
-                                           const float* __restrict__ z,
-                                           const float* __restrict__ noise, int64_t r, int S, int i) {
+// row pointers of one ray (computed once: the per-sample address arithmetic was ~10 % of the instructions)
+struct RayPtrs {
+  const float4* raw;
+  const float* z;
+  const float* nz;   // nullptr: no sigma noise
+};
+__device__ __forceinline__ RayPtrs ray_ptrs(const float* raw, const float* z, const float* noise, int64_t r, int S) {
+  RayPtrs p;
+  p.raw = reinterpret_cast<const float4*>(raw) + r * S;
+  p.z = z + r * S;
+  p.nz = noise ? noise + r * (S - 1) : nullptr;
+  return p;
+}
+// sample i of the ray: everything except z_{i+1} (see link_next)
+__device__ __forceinline__ void load_chunk(RayChunk& c, const RayPtrs& p, int S, int i) {
   if (i < S) {
-    c.rw = ld_stream4(reinterpret_cast<const float4*>(raw) + r * S + i);
-    c.z = z[r * S + i];
-    c.zn = (i + 1 < S) ? z[r * S + i + 1] : c.z;
-    c.nz = (noise != nullptr && i + 1 < S) ? ld_stream(noise + r * (S - 1) + i) : 0.f;
+    c.rw = ld_stream4(p.raw + i);
+    c.z = p.z[i];
+    c.nz = (p.nz != nullptr && i + 1 < S) ? ld_stream(p.nz + i) : 0.f;
   } else {
     c.rw = make_float4(0.f, 0.f, 0.f, 0.f);
-    c.z = c.zn = c.nz = 0.f;
+    c.z = c.nz = 0.f;
   }
+  c.zn = c.z;
+}
+// z_{i+1} of the samples of chunk k: the next lane's z, lane 31 takes lane 0's z of chunk k + 1 (z_first_next)
+__device__ __forceinline__ void link_next(RayChunk& c, float z_first_next, bool has_next, int lane) {
+  float zn = __shfl_down_sync(0xffffffffu, c.z, 1);
+  if (lane == 31) zn = z_first_next;
+  c.zn = has_next ? zn : c.z;
 }
 
 // exclusive product scan over the 32 lanes; returns exclusive prefix, `total` = product of all lanes
@@ -102,10 +126,18 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
   constexpr int N = NCH > 0 ? NCH : 1;
   const int nch = NCH > 0 ? NCH : (S + 31) / 32;
+  const RayPtrs rp = ray_ptrs(raw, z, noise, r, S);
+  float* __restrict__ w_row = weights ? weights + r * S : nullptr;
+  float* __restrict__ d_row = density ? density + r * (S - 1) : nullptr;
   RayChunk ch[N];
   if (NCH > 0) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) load_chunk(ch[k], raw, z, noise, r, S, k * 32 + lane);
+    for (int k = 0; k < N; ++k) load_chunk(ch[k], rp, S, k * 32 + lane);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float zf = __shfl_sync(0xffffffffu, ch[k + 1 < N ? k + 1 : k].z, 0);
+      link_next(ch[k], zf, k * 32 + lane + 1 < S, lane);
+    }
   }
   float T_carry = 1.f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
   int fl = 0;
@@ -113,21 +145,25 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   for (int k = 0; k < nch; ++k) {
     const int i = k * 32 + lane;
     RayChunk c;
-    if (NCH > 0) c = ch[k]; else load_chunk(c, raw, z, noise, r, S, i);
+    if (NCH > 0) c = ch[k];
+    else {      // runtime chunk count (S > 256): z_{i+1} straight from memory
+      load_chunk(c, rp, S, i);
+      if (i + 1 < S) c.zn = rp.z[i + 1];
+    }
     const bool valid = i < S;
     SampleFwd f = sample_fwd(c, i + 1 < S, dnorm, thresh);
     float om = valid ? f.om : 1.f, tot;
     float T = T_carry * warp_excl_prod(om, lane, tot);
     T_carry *= tot;
     float w = valid ? f.alpha * T : 0.f;
-    sr += w * sigmoidf_(c.rw.x);
-    sg += w * sigmoidf_(c.rw.y);
-    sb += w * sigmoidf_(c.rw.z);
+    sr += w * sigmoid_fast(c.rw.x);
+    sg += w * sigmoid_fast(c.rw.y);
+    sb += w * sigmoid_fast(c.rw.z);
     sd += w * c.z;
     sa += w;
     if (valid) {
-      if (weights) weights[r * S + i] = w;
-      if (density && i + 1 < S) density[r * (S - 1) + i] = f.sigma;
+      if (w_row) w_row[i] = w;
+      if (d_row && i + 1 < S) d_row[i] = f.sigma;
       if (nonfinite_bit(c.rw.x) | nonfinite_bit(c.rw.y) | nonfinite_bit(c.rw.z) | nonfinite_bit(c.rw.w) |
           nonfinite_bit(f.sigma)) {   // rare
         fl |= (nanflag(c.rw.x) | nanflag(c.rw.y) | nanflag(c.rw.z) | nanflag(c.rw.w)) << 8;
@@ -169,14 +205,21 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   const float dx = rays_d[r * d_stride], dy = rays_d[r * d_stride + 1], dz = rays_d[r * d_stride + 2];
   const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
   constexpr int N = NCH;
+  const RayPtrs rp = ray_ptrs(raw, z, noise, r, S);
+  float4* __restrict__ g_row = reinterpret_cast<float4*>(g_raw) + r * S;
   RayChunk ch[N];
   float gw_in[N], gden_in[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     const int i = k * 32 + lane;
-    load_chunk(ch[k], raw, z, noise, r, S, i);
+    load_chunk(ch[k], rp, S, i);
     gw_in[k] = (g_weights != nullptr && i < S) ? ld_stream(g_weights + r * S + i) : 0.f;
     gden_in[k] = (g_density != nullptr && i + 1 < S) ? ld_stream(g_density + r * (S - 1) + i) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const float zf = __shfl_sync(0xffffffffu, ch[k + 1 < N ? k + 1 : k].z, 0);
+    link_next(ch[k], zf, k * 32 + lane + 1 < S, lane);
   }
   float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
   if (g_rgb) { gr = g_rgb[r * 3]; gg = g_rgb[r * 3 + 1]; gb = g_rgb[r * 3 + 2]; }
@@ -204,7 +247,7 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
     const bool valid = i < S;
     const RayChunk& c = ch[k];
     SampleFwd f = sample_fwd(c, i + 1 < S, dnorm, thresh);
-    float cr = sigmoidf_(c.rw.x), cg = sigmoidf_(c.rw.y), cb = sigmoidf_(c.rw.z);
+    float cr = sigmoid_fast(c.rw.x), cg = sigmoid_fast(c.rw.y), cb = sigmoid_fast(c.rw.z);
     float G = gr * cr + gg * cg + gb * cb + gd * c.z + ga + gw_in[k];
     // affine map f_i(x) = b + a x, identity on padding lanes
     float a = valid ? f.om : 1.f;
@@ -236,7 +279,7 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
         go.w = (f.pre > 0.f) ? gsig * f.mask : 0.f;
         gdn += galpha * f.sigma * f.e * (c.zn - c.z);
       }
-      reinterpret_cast<float4*>(g_raw)[r * S + i] = go;
+      g_row[i] = go;
     }
   }
   if (g_rays_d != nullptr) {

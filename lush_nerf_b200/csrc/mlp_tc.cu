@@ -285,10 +285,9 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               tmem_st16(tmem_base + tlane + acc_sel * 256u + 32u * rd + 16u * g, pw);
               chain_publish_tmem(B, rd, lane);
               if (tracer && (rd >> 1) == g) chain_trace(C, it, s, 6 + 4 * g + (rd & 1));
-              if (TRAIN) {
+              if (TRAIN && S_.epi != FE_FEATURE) {   // the feature layer is linear: nothing of it is needed backward
                 store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
-                if (S_.epi != FE_FEATURE)
-                  *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd) * 4) = sign_bits(r);
+                *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd) * 4) = sign_bits(r);
               }
               if (S_.epi == FE_TRUNK_LAST) {
 #pragma unroll

@@ -81,7 +81,7 @@ static inline void make_fwd_plan(const MlpLayout& L, FwdPlan& P) {
   int off = 0;
   P.rec_encp = off; off += ENC_BYTES;
   P.rec_h0 = off; off += L.D * H_BYTES;
-  P.rec_feat = off; off += H_BYTES;
+  P.rec_feat = -1;   // the feature layer's output is NOT stashed: the backward never needs it (see mlp_tc_bwd.cu, "T trick")
   P.rec_encv = off; off += ENCV_BYTES;
   P.rec_hv = off; off += HV_BYTES;
   P.rec_mask = off; off += L.D * TROWS * 32;   // 256 relu bits per row per trunk layer
@@ -170,6 +170,9 @@ __host__ __device__ constexpr uint32_t stash_off(uint32_t ncg, uint32_t r, uint3
 }
 // 32 columns (4 groups of 8) of one row of a [128 x 8*ncg] stash blob; c = first column
 __device__ __forceinline__ void store_chunk_global(uint8_t* blob, int ncg, int c, int row, const uint32_t (&pw)[16]) {
+#ifdef LUSH_EXP_NO_STASH   // timing experiment only (results of the backward are garbage): what do the stash stores cost?
+  return;
+#endif
 #pragma unroll
   for (int g = 0; g < 4; ++g)   // written once, read once by a later kernel: streaming stores (evict-first in L2)
     asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(blob + stash_off(ncg, row, (c >> 3) + g)),

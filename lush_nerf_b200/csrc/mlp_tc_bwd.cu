@@ -11,7 +11,8 @@
 //     the SAME stash blobs read as MN-major UMMA operands; fp32 accumulators stay in TMEM across a chunk of
 //     tiles and are flushed once per chunk with fp32 atomics into the flat gradient buffer.  Bias gradients
 //     are column sums taken from the dZ stage in shared memory by the otherwise idle epilogue warps.
-//  3. small SIMT kernels: head gradients (sigma / rgb heads), per-ray reduction of d/d(o, d, viewdirs).
+//  3. small SIMT kernels: head gradients (sigma / rgb heads), encoder backward, per-ray reduction of d/d(o, d, viewdirs).
+#include <algorithm>
 #include "mlp_chain.cuh"
 
 namespace lush {
@@ -20,9 +21,17 @@ constexpr float kGradTarget = 32.f;   // scaled max |g_out|
 
 enum BwdEpi { BE_VIEWS = 0, BE_FEAT = 1, BE_TRUNK = 2, BE_ENC = 3 };
 
-// gstash record (per 128-sample tile): dZv [128 x 128] | dZf [128 x 256] | dZ_0 .. dZ_{D-1} [128 x 256] each
+// gstash record (per 128-sample tile): dZv [128 x 128] | dZ_0 .. dZ_{D-1} [128 x 256] each
+//
+// The "T trick".  The feature layer is linear (feat = H_{D-1} Wf^T + bf feeds the views layer directly), so with
+//   T = dZv^T H_{D-1}  [128 x 256]   and   sv = sum_s dZv  [128]        (Wv' = the feature columns of the views weight)
+//   dW_f       = Wv'^T T              db_f = Wv'^T sv
+//   dW_v[:, feature columns] = T Wf^T + sv bf^T
+// ONE wgrad job (dZv, H_{D-1}) replaces the two jobs (dZf, H_{D-1}) and (dZv, feat): neither feat (forward) nor
+// dZf = dZv Wv' (dgrad) is written to HBM or read back -- 256 KB less traffic per 128-sample tile (13 %) -- and two
+// 128 x 256 x 256 products per step (fv_post_kernel) finish the job.  dZf still exists on chip as a link of the chain.
 struct BwdPlan {
-  int grec_bytes, grec_v, grec_f, grec_l0;
+  int grec_bytes, grec_v, grec_l0;
   int has_enc;          // d/d gamma(x) is produced (two [128 x 64] fp16 blobs per tile: skip layer, layer 0)
   int has_skip_enc;     // ... and the skip-layer blob (slot 0) exists
 };
@@ -46,8 +55,7 @@ struct BPackPlan {
 //               last: d gamma += dZ_0 . W_0            N=64
 static void make_bwd_chain(const MlpLayout& L, bool need_in, ChainPlan& C, BwdPlan& B, BPackPlan& K) {
   B.grec_v = 0;
-  B.grec_f = HV_BYTES;
-  B.grec_l0 = HV_BYTES + H_BYTES;
+  B.grec_l0 = HV_BYTES;
   B.grec_bytes = B.grec_l0 + L.D * H_BYTES;
   B.has_enc = need_in ? 1 : 0;
   B.has_skip_enc = 0;
@@ -67,7 +75,7 @@ static void make_bwd_chain(const MlpLayout& L, bool need_in, ChainPlan& C, BwdPl
     ++n;
   };
   add(128, 1, 0, 0, 1, 0, BE_VIEWS, 0, B.grec_v, 0, 0, 0, 0, 1, L.rgb_w);
-  add(TW, 0, 4, 1, 1, 0, BE_FEAT, 0, B.grec_f, L.views_w, L.W + L.in_ch_v, 0, TW, 0, 0);
+  add(TW, 0, 4, 1, 1, 0, BE_FEAT, 0, -1, L.views_w, L.W + L.in_ch_v, 0, TW, 0, 0);   // dZf: not stored (T trick)
   add(TW, 1, 8, 1, 1, 2, BE_TRUNK, L.D - 1, B.grec_l0 + (L.D - 1) * H_BYTES, L.feat_w, L.W, 0, TW, 2, L.alpha_w);
   int prev_wrote = 1;
   for (int l = L.D - 1; l >= 1; --l) {
@@ -269,7 +277,7 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
                   chain_publish_tmem(B, rd, lane);
                   if (tracer && (rd >> 1) == g) chain_trace(C, it, s, 6 + 4 * g + (rd & 1));
                 }
-                store_chunk_global(grec + S_.off0, S_.N >> 3, col, row, pw);
+                if (S_.epi != BE_FEAT) store_chunk_global(grec + S_.off0, S_.N >> 3, col, row, pw);
               } else {
                 store_chunk_global(genc + (tile * 2 + S_.p0) * (int64_t)ENC_BYTES, 8, col, row, pw);
               }
@@ -289,7 +297,10 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
   if (warp == CH_WARP_MMA0) tmem_dealloc(tmem_base, 512);
 }
 
-// d/dx of the positional encoder from the two d/d gamma(x) blobs (loss-scaled fp16):  one thread per sample
+// d/dx of the positional encoder from the two d/d gamma(x) blobs (loss-scaled fp16):  one thread per sample.
+// sin / cos of 2^l x: exact sincosf at every third octave, the two octaves in between by angle doubling
+// (sin 2a = 2 sin a cos a, cos 2a = 1 - 2 sin^2 a: <= 2 doublings, a few ulp) -- 12 instead of 30 sincosf per sample;
+// the gradients these multiply are fp16 quantities.
 __global__ void __launch_bounds__(128)
 enc_bwd_kernel(const uint8_t* __restrict__ genc, const float* __restrict__ ray_batch, int ray_stride,
                const float* __restrict__ z, const unsigned* __restrict__ scale_buf, float* __restrict__ g_x,
@@ -320,18 +331,18 @@ enc_bwd_kernel(const uint8_t* __restrict__ genc, const float* __restrict__ ray_b
   x[1] = __fadd_rn(rb[1], __fmul_rn(rb[4], zz));
   x[2] = __fadd_rn(rb[2], __fmul_rn(rb[5], zz));
   float gx[3] = {ge[0], ge[1], ge[2]};
-  float f = 1.f;
 #pragma unroll
-  for (int l = 0; l < 10; ++l) {
-    if (l < L_pts) {
+  for (int c = 0; c < 3; ++c) {
+    float f = 1.f, sn = 0.f, cs = 1.f;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float sn, cs;
-        sincosf(x[c] * f, &sn, &cs);
+    for (int l = 0; l < 10; ++l) {
+      if (l < L_pts) {
+        if (l % 3 == 0) sincosf(x[c] * f, &sn, &cs);
+        else { const float s2 = 2.f * sn * cs; cs = fmaf(-2.f * sn, sn, 1.f); sn = s2; }
         gx[c] += f * (cs * ge[3 + 6 * l + c] - sn * ge[3 + 6 * l + 3 + c]);
       }
+      f *= 2.f;
     }
-    f *= 2.f;
   }
   g_x[m * 3 + 0] = gx[0] * inv_scale;
   g_x[m * 3 + 1] = gx[1] * inv_scale;
@@ -349,13 +360,19 @@ constexpr int MAX_WJOBS = 2 * kMaxDepth + 8;
 struct WJob {
   int dz_off, nout;          // dZ blob inside the gstash record, its width (256 | 128)
   int x_off, kin, kin_real;  // X blob inside the forward stash record, padded / real width
-  int64_t w_off;             // dW destination: g_params[w_off + n*fan_in + col0 + k]
-  int fan_in, col0;
+  int64_t w_off;             // dW destination: g_params[w_off + n*fan_in + col0 + k]  (to_aux: aux[n*fan_in + k])
+  int fan_in, col0, to_aux;
   int64_t b_off;             // bias-gradient destination (nout floats) or -1
 };
+constexpr int WG_MAX_UNITS = 6;           // units per CTA in the schedule table
 struct WPlan {
   int njobs, nchunks, tiles_per_chunk;
   WJob jobs[MAX_WJOBS];
+  // Units (job, chunk of tiles) differ in cost by 3x (a trunk layer streams 128 KB per tile, the viewdirs-encoding job
+  // 40 KB), and the kernel is HBM-bound: the host deals them to the persistent CTAs longest-first onto the least loaded
+  // CTA (LPT) and passes the table; a CTA's three roles walk the same list.
+  uint8_t n_of[kNumSMs];
+  uint16_t unit_of[kNumSMs][WG_MAX_UNITS];
 };
 
 static void make_wgrad_plan(const MlpLayout& L, const FwdPlan& P, const BwdPlan& B, int64_t ntiles, WPlan& Wp) {
@@ -364,7 +381,7 @@ static void make_wgrad_plan(const MlpLayout& L, const FwdPlan& P, const BwdPlan&
                  int64_t b_off) {
     WJob& J = Wp.jobs[n++];
     J.dz_off = dz_off; J.nout = nout; J.x_off = x_off; J.kin = kin; J.kin_real = kin_real; J.w_off = w_off;
-    J.fan_in = fan_in; J.col0 = col0; J.b_off = b_off;
+    J.fan_in = fan_in; J.col0 = col0; J.b_off = b_off; J.to_aux = 0;
   };
   // heaviest jobs first (units are dealt round-robin to the persistent CTAs)
   for (int l = L.D - 1; l >= 1; --l) {
@@ -372,25 +389,48 @@ static void make_wgrad_plan(const MlpLayout& L, const FwdPlan& P, const BwdPlan&
     add(B.grec_l0 + l * H_BYTES, TW, P.rec_h0 + (l - 1) * H_BYTES, TW, TW, L.pts_w[l], L.pts_in[l],
         is_skip ? L.in_ch : 0, L.pts_b[l]);
   }
-  add(B.grec_f, TW, P.rec_h0 + (L.D - 1) * H_BYTES, TW, TW, L.feat_w, L.W, 0, L.feat_b);
-  add(B.grec_v, 128, P.rec_feat, TW, TW, L.views_w, L.W + L.in_ch_v, 0, L.views_b);
+  // T = dZv^T H_{D-1} into the aux buffer (+ sv = sum dZv straight into views bias gradient): see "T trick" above
+  add(B.grec_v, 128, P.rec_h0 + (L.D - 1) * H_BYTES, TW, TW, 0, TW, 0, L.views_b);
+  Wp.jobs[n - 1].to_aux = 1;
   add(B.grec_l0, TW, P.rec_encp, 64, L.in_ch, L.pts_w[0], L.pts_in[0], 0, L.pts_b[0]);
   if (L.skip >= 0 && L.skip + 1 < L.D)
     add(B.grec_l0 + (L.skip + 1) * H_BYTES, TW, P.rec_encp, 64, L.in_ch, L.pts_w[L.skip + 1], L.pts_in[L.skip + 1], 0, -1);
   add(B.grec_v, 128, P.rec_encv, 32, L.in_ch_v, L.views_w, L.W + L.in_ch_v, L.W, -1);
   Wp.njobs = n;
-  // ~3 waves of units over the SMs
-  int64_t want_chunks = (3 * (int64_t)kNumSMs + n - 1) / n;
+  // ~4 units per CTA (never more than the table holds)
+  int64_t want_chunks = (4 * (int64_t)kNumSMs) / n;
   if (want_chunks > ntiles) want_chunks = ntiles;
   if (want_chunks < 1) want_chunks = 1;
   Wp.tiles_per_chunk = (int)((ntiles + want_chunks - 1) / want_chunks);
   Wp.nchunks = (int)((ntiles + Wp.tiles_per_chunk - 1) / Wp.tiles_per_chunk);
+  // longest-processing-time-first assignment; cost of a unit = bytes it streams
+  const int nunits = Wp.njobs * Wp.nchunks;
+  static thread_local int order[MAX_WJOBS * 4 * kNumSMs];
+  static thread_local int64_t cost[MAX_WJOBS * 4 * kNumSMs];
+  for (int u = 0; u < nunits; ++u) {
+    const WJob& J = Wp.jobs[u / Wp.nchunks];
+    const int64_t t0 = (int64_t)(u % Wp.nchunks) * Wp.tiles_per_chunk;
+    const int64_t t1 = (t0 + Wp.tiles_per_chunk < ntiles) ? t0 + Wp.tiles_per_chunk : ntiles;
+    cost[u] = (t1 - t0) * (int64_t)(J.nout + J.kin) * 256 + 20000;   // + a per-unit flush / pipeline-fill term
+    order[u] = u;
+  }
+  std::sort(order, order + nunits, [&](int a, int b) { return cost[a] != cost[b] ? cost[a] > cost[b] : a < b; });
+  int64_t load[kNumSMs];
+  const int ncta = nunits < kNumSMs ? nunits : kNumSMs;
+  for (int c = 0; c < kNumSMs; ++c) { load[c] = 0; Wp.n_of[c] = 0; }
+  for (int i = 0; i < nunits; ++i) {
+    int best = -1;
+    for (int c = 0; c < ncta; ++c)
+      if (Wp.n_of[c] < WG_MAX_UNITS && (best < 0 || load[c] < load[best])) best = c;
+    Wp.unit_of[best][Wp.n_of[best]++] = (uint16_t)order[i];
+    load[best] += cost[order[i]];
+  }
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restrict__ gstash,
-                    const unsigned* __restrict__ scale_buf, float* __restrict__ g_params, int64_t ntiles,
-                    int frec_bytes, int grec_bytes, WPlan Wp) {
+                    const unsigned* __restrict__ scale_buf, float* __restrict__ g_params, float* __restrict__ aux,
+                    int64_t ntiles, int frec_bytes, int grec_bytes, WPlan Wp) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full_bar[WG_NSTAGE], empty_bar[WG_NSTAGE], acc_ready, acc_free;
   __shared__ uint32_t tmem_base_s;
@@ -406,13 +446,14 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int nunits = Wp.njobs * Wp.nchunks;
+  const int my_units = Wp.n_of[blockIdx.x];
 
   if (warp == 0) {
     // ---- producer: a 64-sample half of a stash blob is one contiguous run (see stash_off) = the operand image
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      for (int ui = 0; ui < my_units; ++ui) {
+        const int u = Wp.unit_of[blockIdx.x][ui];
         const WJob& J = Wp.jobs[u / Wp.nchunks];
         const int64_t t0 = (int64_t)(u % Wp.nchunks) * Wp.tiles_per_chunk;
         const int64_t t1 = (t0 + Wp.tiles_per_chunk < ntiles) ? t0 + Wp.tiles_per_chunk : ntiles;
@@ -438,7 +479,8 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
     const uint32_t sbase = smem_u32(smem);
     const uint32_t hi = desc_hi(1024u);
     bool first_unit = true;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    for (int ui = 0; ui < my_units; ++ui) {
+      const int u = Wp.unit_of[blockIdx.x][ui];
       const WJob& J = Wp.jobs[u / Wp.nchunks];
       const int64_t t0 = (int64_t)(u % Wp.nchunks) * Wp.tiles_per_chunk;
       const int64_t t1 = (t0 + Wp.tiles_per_chunk < ntiles) ? t0 + Wp.tiles_per_chunk : ntiles;
@@ -470,7 +512,8 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
     const int q = et >> 3, r8 = et & 7;
     const float inv_scale = 1.f / grad_scale_from(scale_buf);
     int stage = 0; uint32_t phase = 0, ready_phase = 0;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    for (int ui = 0; ui < my_units; ++ui) {
+      const int u = Wp.unit_of[blockIdx.x][ui];
       const WJob& J = Wp.jobs[u / Wp.nchunks];
       const int64_t t0 = (int64_t)(u % Wp.nchunks) * Wp.tiles_per_chunk;
       const int64_t t1 = (t0 + Wp.tiles_per_chunk < ntiles) ? t0 + Wp.tiles_per_chunk : ntiles;
@@ -526,7 +569,7 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
       mbar_wait(&acc_ready, ready_phase); ready_phase ^= 1;
       tc_fence_after();
       for (int h = 0; h < J.nout / 128; ++h) {
-        float* dst = g_params + J.w_off + (int64_t)(h * 128 + row) * J.fan_in + J.col0;
+        float* dst = (J.to_aux ? aux : g_params + J.w_off) + (int64_t)(h * 128 + row) * J.fan_in + J.col0;
 #pragma unroll 1
         for (int cc = 0; cc < J.kin; cc += 32) {
           uint32_t r[32];
@@ -698,6 +741,80 @@ ray_grad_reduce_kernel(const float* __restrict__ g_x, const float* __restrict__ 
   if (lane < 3) o[8 + lane] = gv;
 }
 
+// ------------------------------------------------------------------------------------------------
+// stage 2b: the two small products of the "T trick" (once per call): T [128 x 256] = dZv^T H_{D-1} (aux), sv = views
+// bias gradient (already final in g_params).  Weights enter fp16-rounded, as the forward / dgrad kernels used them.
+//   dW_f[j][k] = sum_n Wv[n][j] T[n][k]      db_f[j] = sum_n Wv[n][j] sv[n]
+//   dW_v[n][j] = sum_k T[n][k] Wf[j][k] + sv[n] bf[j]          (j = feature columns 0..255 of the views weight)
+// Block b < 64: a 32 x 32 tile of dW_f (+ db_f from the blocks with k0 = 0); blocks 64..95: a 32 x 32 tile of dW_v.
+// Both operand panels of a tile (32 x K floats each) are staged in shared memory, transposed where that makes the
+// inner loop conflict-free; every thread owns 4 outputs.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float h16r(float v) { return __half2float(__float2half_rn(v)); }
+constexpr int FV_PAD = 33;
+__global__ void __launch_bounds__(256)
+fv_post_kernel(const float* __restrict__ T, const float* __restrict__ params, float* __restrict__ g_params,
+               int64_t views_w, int fan_in_v, int64_t views_b, int64_t feat_w, int64_t feat_b) {
+  extern __shared__ float fv_s[];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;      // ty: 0..7
+  if (blockIdx.x < 64) {
+    // dW_f tile: rows j0..j0+31 (feature units), columns k0..k0+31 (inputs); reduction over n = 0..127
+    const int j0 = (blockIdx.x >> 3) * 32, k0 = (blockIdx.x & 7) * 32;
+    float* a_s = fv_s;                  // [128][FV_PAD]: Wv[n][j0 + jj]
+    float* b_s = fv_s + 128 * FV_PAD;   // [128][FV_PAD]: T[n][k0 + kk]
+    for (int e = tid; e < 128 * 32; e += 256) {
+      const int n = e >> 5, c = e & 31;
+      a_s[n * FV_PAD + c] = h16r(params[views_w + (int64_t)n * fan_in_v + j0 + c]);
+      b_s[n * FV_PAD + c] = T[n * TW + k0 + c];
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int n = 0; n < 128; ++n) {
+      const float t = b_s[n * FV_PAD + tx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(a_s[n * FV_PAD + ty + 8 * q], t, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g_params[feat_w + (int64_t)(j0 + ty + 8 * q) * TW + k0 + tx] = acc[q];
+    if (k0 == 0 && tx == 0) {           // db_f[j] = sum_n Wv[n][j] sv[n]
+      for (int n = 0; n < 128; ++n) {
+        const float sv = g_params[views_b + n];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) accb[q] = fmaf(a_s[n * FV_PAD + ty + 8 * q], sv, accb[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) g_params[feat_b + j0 + ty + 8 * q] = accb[q];
+    }
+  } else {
+    // dW_v tile: rows n0..n0+31 (views units), columns j0..j0+31 (feature inputs); reduction over k = 0..255
+    const int t = blockIdx.x - 64;
+    const int n0 = (t >> 3) * 32, j0 = (t & 7) * 32;
+    float* a_s = fv_s;                  // [256][FV_PAD]: T[n0 + nn][k]   stored [k][nn]
+    float* b_s = fv_s + 256 * FV_PAD;   // [256][FV_PAD]: Wf[j0 + jj][k]  stored [k][jj]
+    for (int e = tid; e < 32 * 256; e += 256) {
+      const int r = e >> 8, k = e & 255;                 // coalesced along k
+      a_s[k * FV_PAD + r] = T[(n0 + r) * TW + k];
+      b_s[k * FV_PAD + r] = h16r(params[feat_w + (int64_t)(j0 + r) * TW + k]);
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = 0; k < 256; ++k) {
+      const float w = b_s[k * FV_PAD + tx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(a_s[k * FV_PAD + ty + 8 * q], w, acc[q]);
+    }
+    const float bf = h16r(params[feat_b + j0 + tx]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int n = n0 + ty + 8 * q;
+      g_params[views_w + (int64_t)n * fan_in_v + j0 + tx] = fmaf(g_params[views_b + n], bf, acc[q]);
+    }
+  }
+}
+constexpr int FV_SMEM = 2 * 256 * FV_PAD * 4;   // 67 584 B
+
 }  // namespace lush
 
 using namespace lush;
@@ -717,7 +834,8 @@ static BwdWorkspace bwd_ws_layout(const MlpLayout& L, int64_t M, bool need_in) {
   size_t off = 0;
   w.bstream = off; off = align256(off + (size_t)C.stream_bytes);
   w.head = off; off = align256(off + (size_t)P.nparam_floats * 4);
-  w.scale = off; off = align256(off + 256);
+  w.scale = off; off = align256(off + 256);          // [loss-scale word (256 B) | aux: T 128 x 256 fp32] zeroed by ONE memset
+  off = align256(off + (size_t)128 * TW * 4);
   w.gx = off; off = align256(off + (size_t)M * 3 * 4);
   w.genc = off; off = align256(off + (size_t)ntiles * 2 * ENC_BYTES);
   w.gstash = off; off = align256(off + (size_t)ntiles * B.grec_bytes);
@@ -748,13 +866,14 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
   __half* bstream = reinterpret_cast<__half*>(ws + w.bstream);
   float* head = reinterpret_cast<float*>(ws + w.head);
   unsigned* scale_buf = reinterpret_cast<unsigned*>(ws + w.scale);
+  float* aux = reinterpret_cast<float*>(ws + w.scale + 256);
   float* gx = reinterpret_cast<float*>(ws + w.gx);
   uint8_t* genc = ws + w.genc;
   uint8_t* gstash = ws + w.gstash;
   const uint8_t* fstash = reinterpret_cast<const uint8_t*>(stash);
   const int64_t ntiles = (M + TROWS - 1) / TROWS;
 
-  int rc = check_cuda(cudaMemsetAsync(scale_buf, 0, 256, st), "mlp_bwd(tc): memset");
+  int rc = check_cuda(cudaMemsetAsync(scale_buf, 0, 256 + (size_t)128 * TW * 4, st), "mlp_bwd(tc): memset");
   if (rc) return rc;
   absmax_kernel<<<(unsigned)(M * 4 / 1024 < 1 ? 1 : (M * 4 / 1024 > 1184 ? 1184 : M * 4 / 1024)), 256, 0, st>>>(g_out, M * 4, scale_buf);
   LUSH_LAUNCH_CHECK("absmax");
@@ -780,9 +899,15 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
     if (rc) return rc;
     const int nunits = Wp.njobs * Wp.nchunks;
     int grid = nunits < kNumSMs ? nunits : kNumSMs;
-    mlp_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(fstash, gstash, scale_buf, g_params, ntiles, P.rec_bytes,
+    mlp_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(fstash, gstash, scale_buf, g_params, aux, ntiles, P.rec_bytes,
                                                        B.grec_bytes, Wp);
     LUSH_LAUNCH_CHECK("mlp_tc_wgrad");
+    rc = check_cuda(cudaFuncSetAttribute(fv_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FV_SMEM),
+                    "mlp_bwd(tc): fv_post smem attr");
+    if (rc) return rc;
+    fv_post_kernel<<<96, 256, FV_SMEM, st>>>(aux, params, g_params, L.views_w, L.W + L.in_ch_v, L.views_b, L.feat_w,
+                                             L.feat_b);
+    LUSH_LAUNCH_CHECK("fv_post");
   }
   {
     const int tpb = (int)((ntiles + 2 * kNumSMs - 1) / (2 * kNumSMs));

@@ -228,7 +228,7 @@ class NeRFAll(nn.Module):
             self._print_flags(int(host.item()), self._overflow_hint())
             self._flags_pending = None
         if self._flags_pending is None:
-            host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+            host = torch.empty(1, dtype=torch.int32, device="cpu", pin_memory=True)
             host.copy_(self._flags, non_blocking=True)
             self._flags.zero_()
             ev = torch.cuda.Event()

@@ -143,7 +143,7 @@ def linspace01(n: int, device) -> torch.Tensor:
     key = (int(n), str(device))
     t = _LINSPACE_CACHE.get(key)
     if t is None:
-        t = torch.linspace(0.0, 1.0, steps=int(n)).to(device)
+        t = torch.linspace(0.0, 1.0, steps=int(n), device="cpu").to(device)   # explicit: the driver sets a CUDA default type
         _LINSPACE_CACHE[key] = t
     return t
 

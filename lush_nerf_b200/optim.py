@@ -48,7 +48,7 @@ class Adam(torch.optim.Optimizer):
                 if self._lr_host[0] is None:
                     raise RuntimeError("run one optimizer step (or _sync_lr) before capturing a CUDA graph")
                 return                    # replays read the device copy; the edit is pushed by the next eager call
-            self._lr.copy_(torch.tensor(cur, dtype=torch.float32), non_blocking=False)
+            self._lr.copy_(torch.tensor(cur, dtype=torch.float32, device="cpu"), non_blocking=False)
             self._lr_host = cur
 
     def _state_of(self, p):

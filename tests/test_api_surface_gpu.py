@@ -114,7 +114,9 @@ def test_bad_image_index_is_defined_and_reported(det_state, capsys, monkeypatch)
     assert torch.isfinite(new_rays).all() and torch.isfinite(ccw).all()
     for bad in (2, 3):                                                   # identity kernel: all 5 rays = the original ray
         assert torch.equal(ccw[bad], torch.tensor([1., 0., 0., 0., 0.], device=DEV))
-        assert torch.equal(new_rays.reshape(6, 5, 3, 2)[bad], rays[bad].expand(5, 3, 2))
+        nr = new_rays.reshape(6, 5, 3, 2)[bad]
+        assert torch.equal(nr[0], rays[bad])                             # slot 0 is the ray itself
+        assert torch.allclose(nr, rays[bad].expand(5, 3, 2), atol=1e-5)  # (o + d) - o with r = v = 0: rounding only
     assert not torch.equal(ccw[1], ccw[2])
     # through NeRFAll.forward the model's guard word collects the bit and the (synchronous) guard raises
     H, W, K = 40, 60, np.array([[50., 0, 30.], [0, 50., 20.], [0, 0, 1]])

@@ -355,11 +355,6 @@ def test_rbk_module_matches_reference_golden(golden, det_state):
     close(ccw, golden["rbk/ccw"], 2e-6, "ccw")
 
 
-@pytest.mark.parametrize("cfg", [
-    dict(num_img=20, N=1024, D=4, W=64, skips=[4], Db=1, Wb=32, M=4, C=64),     # poster configuration
-    dict(num_img=3, N=1, D=2, W=48, skips=[0], Db=2, Wb=24, M=2, C=16),         # skip concat, deeper branches
-    dict(num_img=37, N=777, D=5, W=96, skips=[2], Db=3, Wb=40, M=6, C=33),      # 5 CTAs, ragged last tile, odd widths
-])
 def motion_mlp_torch(rbk, e):
     """The blur kernel's motion network with torch ops on per-ray embeddings, as the reference evaluates it
     (models/lushnerf.py:118-147): e [rows, input_ch] -> (r, v, ccw).  Test-side definition of csrc/motion.cu."""
@@ -382,6 +377,11 @@ def motion_mlp_torch(rbk, e):
     return r, v, w / (torch.sum(w, dim=-1, keepdims=True) + 1e-10)
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(num_img=20, N=1024, D=4, W=64, skips=[4], Db=1, Wb=32, M=4, C=64),     # poster configuration
+    dict(num_img=3, N=1, D=2, W=48, skips=[0], Db=2, Wb=24, M=2, C=16),         # skip concat, deeper branches
+    dict(num_img=37, N=777, D=5, W=96, skips=[2], Db=3, Wb=40, M=6, C=33),      # 5 CTAs, ragged last tile, odd widths
+])
 def test_rbk_motion_fused_matches_torch_layers(cfg):
     """Fused per-image motion network (csrc/motion.cu) vs the same layers applied with torch ops to the per-ray
     embeddings as the reference does (models/lushnerf.py:118-147): outputs and every parameter gradient."""

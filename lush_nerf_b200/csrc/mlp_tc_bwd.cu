@@ -360,7 +360,7 @@ constexpr int MAX_WJOBS = 2 * kMaxDepth + 8;
 struct WJob {
   int dz_off, nout;          // dZ blob inside the gstash record, its width (256 | 128)
   int x_off, kin, kin_real;  // X blob inside the forward stash record, padded / real width
-  int64_t w_off;             // dW destination: g_params[w_off + n*fan_in + col0 + k]  (to_aux: aux[n*fan_in + k])
+  int64_t w_off;             // dW destination: g_params[w_off + n*fan_in + col0 + k]  (to_aux: aux[k*128 + n], transposed)
   int fan_in, col0, to_aux;
   int64_t b_off;             // bias-gradient destination (nout floats) or -1
 };
@@ -397,8 +397,8 @@ static void make_wgrad_plan(const MlpLayout& L, const FwdPlan& P, const BwdPlan&
     add(B.grec_l0 + (L.skip + 1) * H_BYTES, TW, P.rec_encp, 64, L.in_ch, L.pts_w[L.skip + 1], L.pts_in[L.skip + 1], 0, -1);
   add(B.grec_v, 128, P.rec_encv, 32, L.in_ch_v, L.views_w, L.W + L.in_ch_v, L.W, -1);
   Wp.njobs = n;
-  // ~4 units per CTA (never more than the table holds)
-  int64_t want_chunks = (4 * (int64_t)kNumSMs) / n;
+  // ~3 units per CTA (never more than the table holds): every unit pays a pipeline fill and a 65 536-atomic flush
+  int64_t want_chunks = (3 * (int64_t)kNumSMs) / n;
   if (want_chunks > ntiles) want_chunks = ntiles;
   if (want_chunks < 1) want_chunks = 1;
   Wp.tiles_per_chunk = (int)((ntiles + want_chunks - 1) / want_chunks);
@@ -576,8 +576,10 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
           tmem_ld32(tmem_base + tlane + h * 256 + cc, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cc + j < J.kin_real) atomicAdd(dst + cc + j, __uint_as_float(r[j]) * inv_scale);
+          for (int j = 0; j < 32; ++j) {
+            if (J.to_aux) atomicAdd(aux + (cc + j) * 128 + row, __uint_as_float(r[j]) * inv_scale);   // T^T[k][n]: coalesced
+            else if (cc + j < J.kin_real) atomicAdd(dst + cc + j, __uint_as_float(r[j]) * inv_scale);
+          }
         }
       }
       tc_fence_before();
@@ -742,78 +744,48 @@ ray_grad_reduce_kernel(const float* __restrict__ g_x, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 2b: the two small products of the "T trick" (once per call): T [128 x 256] = dZv^T H_{D-1} (aux), sv = views
-// bias gradient (already final in g_params).  Weights enter fp16-rounded, as the forward / dgrad kernels used them.
-//   dW_f[j][k] = sum_n Wv[n][j] T[n][k]      db_f[j] = sum_n Wv[n][j] sv[n]
-//   dW_v[n][j] = sum_k T[n][k] Wf[j][k] + sv[n] bf[j]          (j = feature columns 0..255 of the views weight)
-// Block b < 64: a 32 x 32 tile of dW_f (+ db_f from the blocks with k0 = 0); blocks 64..95: a 32 x 32 tile of dW_v.
-// Both operand panels of a tile (32 x K floats each) are staged in shared memory, transposed where that makes the
-// inner loop conflict-free; every thread owns 4 outputs.
+// stage 2b: the two small products of the "T trick" (once per call).  aux = T^T [256][128] with T = dZv^T H_{D-1}
+// (the wgrad flush of that job writes the transposed orientation: lanes = consecutive n, coalesced atomics);
+// sv = views bias gradient (already final in g_params).  Weights enter fp16-rounded, as the chain kernels used them.
+//   dW_f[j][k] = sum_n Wv[n][j] T^T[k][n]            db_f[j] = sum_n Wv[n][j] sv[n]
+//   dW_v[n][j] = sum_k T^T[k][n] Wf[j][k] + sv[n] bf[j]      (j = feature columns 0..255 of the views weight)
+// One thread per output, no staging: in both products the lanes of a warp read CONSECUTIVE elements of one operand
+// (Wv along j / T^T along n) and the SAME element of the other (a broadcast), 2.4 resident blocks per SM.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float h16r(float v) { return __half2float(__float2half_rn(v)); }
-constexpr int FV_PAD = 33;
 __global__ void __launch_bounds__(256)
-fv_post_kernel(const float* __restrict__ T, const float* __restrict__ params, float* __restrict__ g_params,
+fv_post_kernel(const float* __restrict__ aux, const float* __restrict__ params, float* __restrict__ g_params,
                int64_t views_w, int fan_in_v, int64_t views_b, int64_t feat_w, int64_t feat_b) {
-  extern __shared__ float fv_s[];
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;      // ty: 0..7
-  if (blockIdx.x < 64) {
-    // dW_f tile: rows j0..j0+31 (feature units), columns k0..k0+31 (inputs); reduction over n = 0..127
-    const int j0 = (blockIdx.x >> 3) * 32, k0 = (blockIdx.x & 7) * 32;
-    float* a_s = fv_s;                  // [128][FV_PAD]: Wv[n][j0 + jj]
-    float* b_s = fv_s + 128 * FV_PAD;   // [128][FV_PAD]: T[n][k0 + kk]
-    for (int e = tid; e < 128 * 32; e += 256) {
-      const int n = e >> 5, c = e & 31;
-      a_s[n * FV_PAD + c] = h16r(params[views_w + (int64_t)n * fan_in_v + j0 + c]);
-      b_s[n * FV_PAD + c] = T[n * TW + k0 + c];
+  const float* __restrict__ Tt = aux;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < TW * TW) {                                   // dW_f[j][k]: lanes along j
+    const int k = e / TW, j = e - k * TW;
+    const float* wv = params + views_w + j;
+    const float* tk = Tt + k * 128;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+    for (int n = 0; n < 128; n += 2) {
+      a0 = fmaf(h16r(wv[(int64_t)n * fan_in_v]), tk[n], a0);
+      a1 = fmaf(h16r(wv[(int64_t)(n + 1) * fan_in_v]), tk[n + 1], a1);
     }
-    __syncthreads();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int n = 0; n < 128; ++n) {
-      const float t = b_s[n * FV_PAD + tx];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = fmaf(a_s[n * FV_PAD + ty + 8 * q], t, acc[q]);
+    g_params[feat_w + (int64_t)j * TW + k] = a0 + a1;
+  } else if (e < TW * TW + 128 * TW) {                 // dW_v[n][j]: lanes along n
+    const int q = e - TW * TW, j = q >> 7, n = q & 127;
+    const float* wf = params + feat_w + (int64_t)j * TW;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < TW; k += 2) {
+      a0 = fmaf(Tt[k * 128 + n], h16r(wf[k]), a0);
+      a1 = fmaf(Tt[(k + 1) * 128 + n], h16r(wf[k + 1]), a1);
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) g_params[feat_w + (int64_t)(j0 + ty + 8 * q) * TW + k0 + tx] = acc[q];
-    if (k0 == 0 && tx == 0) {           // db_f[j] = sum_n Wv[n][j] sv[n]
-      for (int n = 0; n < 128; ++n) {
-        const float sv = g_params[views_b + n];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) accb[q] = fmaf(a_s[n * FV_PAD + ty + 8 * q], sv, accb[q]);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) g_params[feat_b + j0 + ty + 8 * q] = accb[q];
-    }
-  } else {
-    // dW_v tile: rows n0..n0+31 (views units), columns j0..j0+31 (feature inputs); reduction over k = 0..255
-    const int t = blockIdx.x - 64;
-    const int n0 = (t >> 3) * 32, j0 = (t & 7) * 32;
-    float* a_s = fv_s;                  // [256][FV_PAD]: T[n0 + nn][k]   stored [k][nn]
-    float* b_s = fv_s + 256 * FV_PAD;   // [256][FV_PAD]: Wf[j0 + jj][k]  stored [k][jj]
-    for (int e = tid; e < 32 * 256; e += 256) {
-      const int r = e >> 8, k = e & 255;                 // coalesced along k
-      a_s[k * FV_PAD + r] = T[(n0 + r) * TW + k];
-      b_s[k * FV_PAD + r] = h16r(params[feat_w + (int64_t)(j0 + r) * TW + k]);
-    }
-    __syncthreads();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int k = 0; k < 256; ++k) {
-      const float w = b_s[k * FV_PAD + tx];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = fmaf(a_s[k * FV_PAD + ty + 8 * q], w, acc[q]);
-    }
-    const float bf = h16r(params[feat_b + j0 + tx]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int n = n0 + ty + 8 * q;
-      g_params[views_w + (int64_t)n * fan_in_v + j0 + tx] = fmaf(g_params[views_b + n], bf, acc[q]);
-    }
+    g_params[views_w + (int64_t)n * fan_in_v + j] = fmaf(g_params[views_b + n], h16r(params[feat_b + j]), a0 + a1);
+  } else if (e < TW * TW + 128 * TW + TW) {            // db_f[j]
+    const int j = e - TW * TW - 128 * TW;
+    float acc = 0.f;
+    for (int n = 0; n < 128; ++n) acc = fmaf(h16r(params[views_w + (int64_t)n * fan_in_v + j]), g_params[views_b + n], acc);
+    g_params[feat_b + j] = acc;
   }
 }
-constexpr int FV_SMEM = 2 * 256 * FV_PAD * 4;   // 67 584 B
 
 }  // namespace lush
 
@@ -873,7 +845,7 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
   const uint8_t* fstash = reinterpret_cast<const uint8_t*>(stash);
   const int64_t ntiles = (M + TROWS - 1) / TROWS;
 
-  int rc = check_cuda(cudaMemsetAsync(scale_buf, 0, 256 + (size_t)128 * TW * 4, st), "mlp_bwd(tc): memset");
+  int rc = check_cuda(cudaMemsetAsync(scale_buf, 0, 256 + (size_t)128 * TW * 4, st), "mlp_bwd(tc): memset");   // scale word + T^T
   if (rc) return rc;
   absmax_kernel<<<(unsigned)(M * 4 / 1024 < 1 ? 1 : (M * 4 / 1024 > 1184 ? 1184 : M * 4 / 1024)), 256, 0, st>>>(g_out, M * 4, scale_buf);
   LUSH_LAUNCH_CHECK("absmax");
@@ -902,11 +874,8 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
     mlp_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(fstash, gstash, scale_buf, g_params, aux, ntiles, P.rec_bytes,
                                                        B.grec_bytes, Wp);
     LUSH_LAUNCH_CHECK("mlp_tc_wgrad");
-    rc = check_cuda(cudaFuncSetAttribute(fv_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FV_SMEM),
-                    "mlp_bwd(tc): fv_post smem attr");
-    if (rc) return rc;
-    fv_post_kernel<<<96, 256, FV_SMEM, st>>>(aux, params, g_params, L.views_w, L.W + L.in_ch_v, L.views_b, L.feat_w,
-                                             L.feat_b);
+    fv_post_kernel<<<(TW * TW + 128 * TW + TW + 255) / 256, 256, 0, st>>>(aux, params, g_params, L.views_w, L.W + L.in_ch_v,
+                                                                         L.views_b, L.feat_w, L.feat_b);
     LUSH_LAUNCH_CHECK("fv_post");
   }
   {

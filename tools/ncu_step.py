@@ -2,7 +2,7 @@
 """Summarise an `ncu --set full` capture of the tcgen05 MLP kernels of ONE bench.py training step:
     ncu --set full --clock-control none --import-source on -k regex:mlp_tc --launch-skip 18 -c 6 \\
         -o gpurun_out/ncu_step python bench.py --steps 2 --warmup 3 --no-render --no-cpu-baseline
-    python tools/ncu_step.py gpurun_out/ncu_step.ncu-rep profiles/r01_ncu_mlp_step.json
+    python tools/ncu_step.py gpurun_out/ncu_step.ncu-rep profiles/rNN_ncu_mlp_step.json
 """
 import csv, io, json, subprocess, sys
 rep, out = sys.argv[1], sys.argv[2]

@@ -169,9 +169,15 @@ __host__ __device__ constexpr uint32_t stash_off(uint32_t ncg, uint32_t r, uint3
   return (r >> 6) * (ncg * 1024u) + cg * 1024u + (r & 63u) * 16u;
 }
 // 32 columns (4 groups of 8) of one row of a [128 x 8*ncg] stash blob; c = first column
+#ifdef LUSH_EXP_STASH_LOCAL
+static __device__ uint8_t g_exp_stash_window[128 * 65536];   // 8 MB: stays in L2
+#endif
 __device__ __forceinline__ void store_chunk_global(uint8_t* blob, int ncg, int c, int row, const uint32_t (&pw)[16]) {
 #ifdef LUSH_EXP_NO_STASH   // timing experiment only (results of the backward are garbage): what do the stash stores cost?
   return;
+#endif
+#ifdef LUSH_EXP_STASH_LOCAL   // timing experiment only: the same store instructions, but into an L2-resident window per
+  blob = g_exp_stash_window + (blockIdx.x & 127) * 65536;   // CTA (no DRAM write traffic): instruction cost vs traffic cost
 #endif
 #pragma unroll
   for (int g = 0; g < 4; ++g)   // written once, read once by a later kernel: streaming stores (evict-first in L2)

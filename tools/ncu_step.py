@@ -16,6 +16,7 @@ want = {"gpu__time_duration.sum": "time_ms", "dram__bytes_read.sum": "dram_read"
         "sm__cycles_elapsed.max": "sm_cycles", "launch__grid_size": "grid", "launch__registers_per_thread": "regs"}
 units = dict(zip(h, rows[1]))
 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0, "second": 1e3}   # -> ms
 kernels, total = [], 0.0
 for r in rows[2:]:
     d = dict(zip(h, r))
@@ -25,6 +26,8 @@ for r in rows[2:]:
             v = float(d[m].replace(",", ""))
             if name.startswith("dram_r") or name.startswith("dram_w"):
                 v *= scale.get(units[m], 1.0)
+            if name == "time_ms":
+                v *= tscale.get(units[m], 1.0)
             k[name] = v
     k["dram_bytes"] = k.get("dram_read", 0.0) + k.get("dram_write", 0.0)
     total += k["dram_bytes"]

@@ -282,13 +282,18 @@ class Trainer:
     def check_numerics(self):
         """Deferred NaN/Inf guard for graph mode: one device->host read of the model's flag word."""
         f = getattr(self.model, "_flags", None)
-        if f is not None:
-            bits = int(f.item())
-            f.zero_()
-            if bits:
-                self.model._print_flags(bits, self.model._overflow_hint())
-            return bits
-        return 0
+        if f is None:
+            return 0
+        bits = int(f.item())
+        f.zero_()
+        pend = getattr(self.model, "_flags_pending", None)     # a copy the lazy guard took but has not looked at yet
+        if pend is not None:
+            pend[1].synchronize()
+            bits |= int(pend[0].item())
+            self.model._flags_pending = None
+        if bits:
+            self.model._print_flags(bits, self.model._overflow_hint())
+        return bits
 
     def set_lr(self, decay_steps=250000, decay_rate=0.1):
         lr = self.lrate * (decay_rate ** (self.global_step / decay_steps))  # reference :681-685

@@ -102,3 +102,41 @@ def test_multi_tensor_adam_matches_torch_adam():
     assert set(st) == set(st_ref) and 2 not in st
     assert float(st[4]["step"]) == 9.0 and float(st[0]["step"]) == 12.0
     assert rel_l2(st[3]["exp_avg_sq"], st_ref[3]["exp_avg_sq"]) < 2e-6
+
+
+def test_index_batches_equal_table_batches():
+    """Trainer.set_scene + {images_idx, pix_idx} batches (rays, targets and mask bits staged on the device by ONE kernel
+    from the resident poses / images / masks) must be the same training step as the reference's batch form
+    {rays, rgbsf, fq_mask, images_idx} sliced from a host-side ray table (run_lushnerf.py:538-616)."""
+    from lush_nerf_b200.synthetic import synthetic_poses
+    from lush_nerf_b200.utils.run_lushnerf_helpers import get_rays_np
+    tr_i, _ = _make()
+    tr_t, _ = _make()
+    V, n = 5, 96
+    g = torch.Generator().manual_seed(5)
+    poses = torch.from_numpy(synthetic_poses(V, 0))
+    images = torch.rand(V, H, W, 3, generator=g)
+    masks = torch.rand(V, H, W, generator=g) < 0.5
+    K = tr_i.K
+    tr_i.set_scene(poses, images, masks)
+    for step in range(3):
+        v = torch.randint(0, V, (n, 1), generator=g)
+        p = torch.randint(0, H * W, (n,), generator=g)
+        rays = torch.empty(n, 3, 2)
+        for i in range(n):
+            ro, rd = get_rays_np(H, W, K, poses[v[i, 0]].numpy())
+            rays[i, :, 0] = torch.from_numpy(np.ascontiguousarray(ro.reshape(-1, 3)[p[i]])).float()
+            rays[i, :, 1] = torch.from_numpy(rd.reshape(-1, 3)[p[i]].astype(np.float32))
+        table = dict(rays=rays.cuda(), rgbsf=images.reshape(V, -1, 3)[v[:, 0], p].cuda(),
+                     fq_mask=masks.reshape(V, -1)[v[:, 0], p].cuda(), images_idx=v.cuda())
+        li = float(tr_i.step(dict(images_idx=v.cuda(), pix_idx=p.cuda())).item())
+        lt = float(tr_t.step(table).item())
+        assert abs(li - lt) <= 2e-5 * max(1.0, abs(lt)), (step, li, lt)
+    assert tr_i.check_numerics() == 0
+    with pytest.raises(RuntimeError):
+        tr_t.step(dict(images_idx=v.cuda(), pix_idx=p.cuda()))          # no scene tables set
+    # an out-of-range pixel index is clamped, flagged, and surfaces as IndexError from the guard
+    bad = dict(images_idx=v.cuda(), pix_idx=(p + H * W).cuda())
+    tr_i.step(bad)
+    with pytest.raises(IndexError):
+        tr_i.check_numerics()

@@ -5,8 +5,9 @@
 //   * accumulators are DOUBLE-BUFFERED in tensor memory (2 x 256 fp32 columns, alternating by step): the tensor
 //     core works on step s+1 while the epilogue warps are still draining step s;
 //   * the fp16 activations that feed the next step live in ONE tile [128 x 256] in TENSOR memory (written in place
-//     into the first 128 columns of the accumulator just drained, read by TS-mode MMAs; no hazard: the epilogue of
-//     step s starts only after every MMA of step s has completed).  ChRing::ACT_IN_TMEM = false selects the older
+//     into the accumulator just drained: every epilogue warp packs its 32-column chunk into the first 16 columns of
+//     that same chunk, so nobody overwrites columns another warp has yet to load; read by TS-mode MMAs; no hazard: the
+//     epilogue of step s starts only after every MMA of step s has completed).  ChRing::ACT_IN_TMEM = false selects the older
 //     shared-memory activation tile in the UMMA operand layout;
 //   * the rest of shared memory is a ring (ChRing: 4 x 40 KB forward, 4 x 32 KB dgrad) of weight blocks [N x 64 K] streamed with bulk async
 //     copies (TMA engine) in exactly the order the MMAs consume them; the bias rides in the MMA as one extra
@@ -48,7 +49,7 @@ constexpr int CH_MAX_NSTAGE = 4;
 //            block of every step arrived ~2 000 cycles after its activations were ready)
 template <int NSTAGE_, int STAGE_BYTES_, bool ACT_IN_TMEM_ = false>
 struct ChRing {
-  // true: the epilogue writes the next step's A operand into TENSOR memory (in place, into the first 128 columns of the
+  // true: the epilogue writes the next step's A operand into TENSOR memory (in place, inside the
   // accumulator it has just drained) and the hidden-block MMAs read it from there (TS mode): no activation stores /
   // operand reads / proxy fences on the shared-memory port, which is the contended resource of these kernels
   static constexpr bool ACT_IN_TMEM = ACT_IN_TMEM_;
@@ -227,7 +228,9 @@ __device__ __forceinline__ void mma_ss(uint32_t tacc, uint32_t a_lo, uint32_t b_
 #undef LUSH_SS_FIRST
 #undef LUSH_SS_NEXT
 
-// same with the A operand in tensor memory: 8 columns (16 fp16) of all 128 lanes per K=16, consecutive columns
+// same with the A operand in tensor memory: 8 columns (16 fp16) of all 128 lanes per K=16.  The 64 K-values of one
+// activation group sit where the two epilogue warpgroups found their accumulator chunks: K [0,32) in columns [0,16) of the
+// group's 64-column slot, K [32,64) in columns [32,48)
 #define LUSH_TS_FIRST                                                       \
   "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t.reg .b32 at, bl;\n\t"            \
   "setp.ne.b32 p, %6, 0;\n\t"                                               \
@@ -235,13 +238,13 @@ __device__ __forceinline__ void mma_ss(uint32_t tacc, uint32_t a_lo, uint32_t b_
   "mov.b64 db, {bl, %3};\n\t"                                              \
   "tcgen05.mma.cta_group::1.kind::f16 [%0], [at], db, %5, p;\n\t"          \
   "setp.eq.b32 p, %6, %6;\n\t"
-#define LUSH_TS_NEXT                                                        \
-  "add.u32 at, at, 8;\n\tadd.u32 bl, bl, %4;\n\t"                           \
+#define LUSH_TS_NEXT(STEP)                                                  \
+  "add.u32 at, at, " #STEP ";\n\tadd.u32 bl, bl, %4;\n\t"                   \
   "mov.b64 db, {bl, %3};\n\t"                                              \
   "tcgen05.mma.cta_group::1.kind::f16 [%0], [at], db, %5, p;\n\t"
 __device__ __forceinline__ void mma_ts4(uint32_t tacc, uint32_t a_tmem, uint32_t b_lo, uint32_t hi, uint32_t bk16,
                                         uint32_t idesc, uint32_t acc) {
-  asm volatile(LUSH_TS_FIRST LUSH_TS_NEXT LUSH_TS_NEXT LUSH_TS_NEXT "}" ::"r"(tacc), "r"(a_tmem), "r"(b_lo), "r"(hi),
+  asm volatile(LUSH_TS_FIRST LUSH_TS_NEXT(8) LUSH_TS_NEXT(24) LUSH_TS_NEXT(8) "}" ::"r"(tacc), "r"(a_tmem), "r"(b_lo), "r"(hi),
                "r"(bk16), "r"(idesc), "r"(acc)
                : "memory");
 }
@@ -317,8 +320,8 @@ __device__ __forceinline__ void chain_mma_issuer(ChainBars& B, uint8_t* smem, ui
             else if (S.enc_slices == 1) { mma_ss<2>(tacc, e_lo, b_lo, hi128, A_K16, B_K16, idesc, acc); acc = 1; b_lo += 2u * B_K16; }
           }
           if (has_h) {
-            if (R::ACT_IN_TMEM)   // A = packed activations in the first 128 columns of the OTHER accumulator buffer
-              mma_ts4(tacc, tmem_base + (acc_sel ^ 1u) * 256u + grp * 32u, b_lo, hi128, B_K16, idesc, acc);
+            if (R::ACT_IN_TMEM)   // A = packed activations inside the OTHER accumulator buffer, group grp in its slot
+              mma_ts4(tacc, tmem_base + (acc_sel ^ 1u) * 256u + grp * 64u, b_lo, hi128, B_K16, idesc, acc);
             else
               mma_ss<4>(tacc, act_lo + grp * 4u * A_K16, b_lo, hi128, A_K16, B_K16, idesc, acc);
           }

@@ -278,8 +278,6 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
             uint32_t (&r)[32] = hb ? rb2 : ra;
             const int col = 64 * rd + 32 * g;         // first output column of my chunk
             tmem_ld_wait();
-            // warps w of the two warpgroups own the same 32 rows: both have round rd in registers from here on
-            if (S_.writes_a) named_bar_sync(1 + (warp & 3), 64);
             if (rd + 1 < nround) tmem_ld32(tacc + 64u * (rd + 1), hb ? ra : rb2);
             else {                                    // everything of mine is in registers
               chain_release_acc(B, (int)acc_sel, lane);
@@ -289,10 +287,9 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               // critical path first: fp16 -> activation tile -> publish; everything else rides behind the hand-off
               if (S_.epi == FE_FEATURE) pack_chunk<false, false>(r, pw);
               else pack_chunk<true, false>(r, pw);
-              // A operand of the next step: 16 packed columns into the accumulator buffer being drained, at
-              // columns [32 rd + 16 g, +16) -- accumulator columns that were loaded in a round <= rd (the pair barrier
-              // above covers the one case where the partner warp of the other warpgroup loaded them, round 0)
-              tmem_st16(tmem_base + tlane + acc_sel * 256u + 32u * rd + 16u * g, pw);
+              // A operand of the next step: 16 packed columns over the first 16 columns of the very chunk this warp has
+              // just loaded -- no other warp ever reads those as accumulator, so the two warpgroups need no barrier
+              tmem_st16(tacc + 64u * rd, pw);
               chain_publish_tmem(B, rd, lane);
               if (tracer && (rd >> 1) == g) chain_trace(C, it, s, 6 + 4 * g + (rd & 1));
               if (TRAIN && S_.epi != FE_FEATURE) {   // the feature layer is linear: nothing of it is needed backward

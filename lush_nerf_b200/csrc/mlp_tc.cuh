@@ -186,8 +186,4 @@ __device__ __forceinline__ void store_chunk_global(uint8_t* blob, int ncg, int c
                  : "memory");
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 }  // namespace lush

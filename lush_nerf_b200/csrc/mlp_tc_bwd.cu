@@ -251,8 +251,6 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
               uint32_t (&r)[32] = hb ? rb2 : ra;
               const int col = 64 * rd + 32 * g;
               tmem_ld_wait();
-              // warps w of the two warpgroups own the same 32 rows: both have round rd in registers from here on
-              if (S_.writes_a) named_bar_sync(1 + (warp & 3), 64);
               if (rd + 1 < nround) tmem_ld32(tacc + 64u * (rd + 1), hb ? ra : rb2);
               else {
                 chain_release_acc(B, (int)acc_sel, lane);
@@ -272,8 +270,8 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
               }
               if (S_.epi != BE_ENC) {
                 if (S_.writes_a) {
-                  // A operand of the next step(s): packed columns [32 rd + 16 g, +16) of the buffer being drained
-                  tmem_st16(tmem_base + tlane + acc_sel * 256u + 32u * rd + 16u * g, pw);
+                  // A operand of the next step(s): packed over the first 16 columns of my own chunk of the buffer being drained
+                  tmem_st16(tacc + 64u * rd, pw);
                   chain_publish_tmem(B, rd, lane);
                   if (tracer && (rd >> 1) == g) chain_trace(C, it, s, 6 + 4 * g + (rd & 1));
                 }

@@ -269,6 +269,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         const uint32_t tacc = tmem_base + tlane + acc_sel * 256u + 32u * g;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
         uint32_t ra[32], rb2[32], pw[16];
+        uint32_t mkeep = 0;
         tmem_ld32(tacc, ra);
 #pragma unroll 1
         for (int rd2 = 0; rd2 < nround; rd2 += 2) {
@@ -294,7 +295,10 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               if (tracer && (rd >> 1) == g) chain_trace(C, it, s, 6 + 4 * g + (rd & 1));
               if (TRAIN && S_.epi != FE_FEATURE) {   // the feature layer is linear: nothing of it is needed backward
                 store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
-                *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd) * 4) = sign_bits(r);
+                // ReLU bits: one word per round; the two rounds of a pair leave as one 8-byte store
+                if (hb == 0) mkeep = sign_bits(r);
+                else *reinterpret_cast<uint2*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd2) * 4) =
+                         make_uint2(mkeep, sign_bits(r));
               }
               if (S_.epi == FE_TRUNK_LAST) {
 #pragma unroll
@@ -320,7 +324,10 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               if (TRAIN) {
                 pack_chunk<true, false>(r, pw);
                 store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
-                *reinterpret_cast<uint32_t*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd) * 4) = sign_bits(r);
+                // ReLU bits: one word per round; the two rounds of a pair leave as one 8-byte store
+                if (hb == 0) mkeep = sign_bits(r);
+                else *reinterpret_cast<uint2*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd2) * 4) =
+                         make_uint2(mkeep, sign_bits(r));
               }
             }
           }

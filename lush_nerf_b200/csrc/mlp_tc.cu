@@ -270,6 +270,7 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
         uint32_t ra[32], rb2[32], pw[16];
         uint32_t mkeep = 0;
+        uint2 mpair = make_uint2(0u, 0u);
         tmem_ld32(tacc, ra);
 #pragma unroll 1
         for (int rd2 = 0; rd2 < nround; rd2 += 2) {
@@ -295,10 +296,12 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               if (tracer && (rd >> 1) == g) chain_trace(C, it, s, 6 + 4 * g + (rd & 1));
               if (TRAIN && S_.epi != FE_FEATURE) {   // the feature layer is linear: nothing of it is needed backward
                 store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
-                // ReLU bits: one word per round; the two rounds of a pair leave as one 8-byte store
+                // ReLU bits: one word per round, stored ONCE per step as [warpgroup][row][16 bytes] -- a warp writes 512
+                // contiguous bytes (four 4-byte stores per thread at a 32-byte stride cost 7 % of this kernel)
                 if (hb == 0) mkeep = sign_bits(r);
-                else *reinterpret_cast<uint2*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd2) * 4) =
-                         make_uint2(mkeep, sign_bits(r));
+                else if (rd2 == 0) { mpair.x = mkeep; mpair.y = sign_bits(r); }
+                else *reinterpret_cast<uint4*>(rec + S_.off1 + (g * TROWS + row) * 16) =
+                         make_uint4(mpair.x, mpair.y, mkeep, sign_bits(r));
               }
               if (S_.epi == FE_TRUNK_LAST) {
 #pragma unroll
@@ -324,10 +327,9 @@ mlp_tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
               if (TRAIN) {
                 pack_chunk<true, false>(r, pw);
                 store_chunk_global(rec + S_.off0, S_.N >> 3, col, row, pw);
-                // ReLU bits: one word per round; the two rounds of a pair leave as one 8-byte store
+                // ReLU bits of the 128-wide views layer: [warpgroup][row][8 bytes]
                 if (hb == 0) mkeep = sign_bits(r);
-                else *reinterpret_cast<uint2*>(rec + S_.off1 + row * (S_.N >> 3) + (nround * g + rd2) * 4) =
-                         make_uint2(mkeep, sign_bits(r));
+                else *reinterpret_cast<uint2*>(rec + S_.off1 + (g * TROWS + row) * 8) = make_uint2(mkeep, sign_bits(r));
               }
             }
           }

@@ -84,8 +84,8 @@ static inline void make_fwd_plan(const MlpLayout& L, FwdPlan& P) {
   P.rec_feat = -1;   // the feature layer's output is NOT stashed: the backward never needs it (see mlp_tc_bwd.cu, "T trick")
   P.rec_encv = off; off += ENCV_BYTES;
   P.rec_hv = off; off += HV_BYTES;
-  P.rec_mask = off; off += L.D * TROWS * 32;   // 256 relu bits per row per trunk layer
-  P.rec_maskv = off; off += TROWS * 16;        // 128 bits per row for the views layer
+  P.rec_mask = off; off += L.D * TROWS * 32;   // 256 relu bits per row per trunk layer: [layer][warpgroup][row][16 B]
+  P.rec_maskv = off; off += TROWS * 16;        // 128 bits per row for the views layer: [warpgroup][row][8 B]
   P.rec_bytes = off;
 }
 

@@ -160,13 +160,14 @@ struct DgSmem {
 // stage 1: fused dgrad chain (one instance of the skeleton in mlp_chain.cuh)
 // ------------------------------------------------------------------------------------------------
 // ReLU mask words of `row` for the epilogue of one dgrad step: warpgroup g owns columns [64 rd + 32 g, +32) of every
-// round rd; the forward kernel stores a row's words as [g][rd], i.e. one aligned 16-byte (trunk) / 8-byte (views) load.
+// round rd; the forward kernel stores a layer's words as [g][row][rd], i.e. one aligned 16-byte (trunk) / 8-byte (views)
+// load, contiguous over the rows of a warp.
 __device__ __forceinline__ uint4 dgrad_mask_words(const uint8_t* frec, const FwdPlan& P, int epi, int p0, int row, int g) {
   uint4 m = make_uint4(0u, 0u, 0u, 0u);
   if (epi == BE_TRUNK) {
-    m = *reinterpret_cast<const uint4*>(frec + P.rec_mask + (p0 * TROWS + row) * 32 + g * 16);
+    m = *reinterpret_cast<const uint4*>(frec + P.rec_mask + ((p0 * 2 + g) * TROWS + row) * 16);
   } else if (epi == BE_VIEWS) {
-    const uint2 v = *reinterpret_cast<const uint2*>(frec + P.rec_maskv + row * 16 + g * 8);
+    const uint2 v = *reinterpret_cast<const uint2*>(frec + P.rec_maskv + (g * TROWS + row) * 8);
     m.x = v.x; m.y = v.y;
   }
   return m;

@@ -313,13 +313,16 @@ class _MLP(torch.autograd.Function):
     autograd routes their gradients (returned as views of one flat gradient buffer)."""
 
     @staticmethod
-    def forward(ctx, ray_batch, z, desc, impl, flat, numels, *params):
+    def forward(ctx, ray_batch, z, desc, impl, flat, numels, track, *params):
         rb, z = _f32c(ray_batch), _f32c(z)
         R, S = z.shape
         C = 4 if desc.out_mode == 0 else 3
         out = _empty((R, S, C), rb)
         L = lib()
-        training = any(ctx.needs_input_grad)  # grad mode is off inside forward(); this is the right test
+        # `track` = grad mode of the CALLER (inside forward() it is always off, and ctx.needs_input_grad only says which
+        # inputs require grad, also under torch.no_grad()): without it a no_grad render would run the training kernel
+        # and write a 4.7 KB/sample activation stash nobody reads
+        training = bool(track) and any(ctx.needs_input_grad)
         stash = None
         if training:
             nb = L.lush_mlp_stash_bytes(byref(desc), R, S, impl)
@@ -350,21 +353,21 @@ class _MLP(torch.autograd.Function):
                                  ptr(g_flat), ptr(g_rb), ptr(ws), wb, R, S, impl, stream()), "lush_mlp_bwd")
         _arena_done(g_flat)
         grads, off = [], 0
-        for n, shp, need in zip(numels, shapes, ctx.needs_input_grad[6:]):
+        for n, shp, need in zip(numels, shapes, ctx.needs_input_grad[7:]):
             grads.append(g_flat[off:off + n].view(shp) if need else None)
             off += n
         if g_rb is not None and rb.shape[1] != 11:
             full = torch.zeros_like(rb)
             full[:, :11] = g_rb
             g_rb = full
-        return (g_rb, None, None, None, None, None, *grads)
+        return (g_rb, None, None, None, None, None, None, *grads)
 
 
 def mlp_apply(ray_batch, z, desc: MlpDesc, impl: int, flat: torch.Tensor, params):
     if not ray_batch.is_cuda:
         raise RuntimeError("lush_nerf_b200 MLP needs CUDA tensors; there is no CPU fallback")
     numels = [p.numel() for p in params]
-    return _MLP.apply(ray_batch, z.detach(), desc, int(impl), flat, numels, *params)
+    return _MLP.apply(ray_batch, z.detach(), desc, int(impl), flat, numels, torch.is_grad_enabled(), *params)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -548,6 +548,25 @@ def test_mlp_golden_outputs_through_public_mlpforward(golden, det_state):
     close(out[:, 0, :], golden["mlp/coarse/out"], 5e-5, "NeRF.forward golden")
 
 
+def test_small_mlp_big_row_tiles_bit_identical(det_state):
+    """From 4096 rows on (a render chunk) the fused noise-MLP forward runs 32 rows per CTA instead of 8 (csrc/mlp_small.cu,
+    SM_BIG_ROWS): same FMA order per output, so the result must equal the small-tile kernel's bit for bit -- and the
+    oracle's on a slice."""
+    nets, _ = det_state
+    D, W, mode = 4, 128, 1
+    R = 4096 + 37                      # a ragged last tile too
+    rb, z = mlp_case("noise", R, 1, 11)
+    desc = _lib.MlpDesc(D, W, 10, 4, 4, mode)
+    shapes = O.mlp_param_shapes(D, W, 63, 27, 4)
+    flat = torch.cat([nets["noise"][n].reshape(-1) for n, _ in shapes]).to(DEV)
+    with torch.no_grad():
+        big = ops.mlp_apply(rb.to(DEV), z.to(DEV), desc, 0, flat, [])
+        parts = [ops.mlp_apply(rb[a:a + 2048].to(DEV), z[a:a + 2048].to(DEV), desc, 0, flat, []) for a in range(0, R, 2048)]
+    assert torch.equal(big, torch.cat(parts, 0))
+    ref = O.mlp_on_rays(nets["noise"], rb[:64], z[:64], D, W, 10, 4, 4, mode)
+    close(big[:64], ref, 3e-5 * max(1.0, ref.abs().max().item()), "small mlp (32-row tiles) vs oracle")
+
+
 @pytest.mark.parametrize("R,S", [(1024, 1), (77, 3)])
 def test_small_mlp_fused_backward_vs_oracle(det_state, R, S):
     """Noise MLP with detached inputs (the model's call pattern): fused forward AND fused backward kernels

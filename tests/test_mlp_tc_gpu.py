@@ -5,6 +5,8 @@ Stated tolerance (north_star: "fp32/TF32 tolerance, e.g. max-abs 1e-3 on rgb"): 
   * raw network outputs: <= 4e-3 of the output scale vs the exact-fp32 SIMT path on the same inputs
   * rendered rgb_map / rgb0 (random-init-like nets, sigma head x30): max-abs <= 1e-3, depth <= 1e-2
 """
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -47,6 +49,39 @@ def test_tc_forward_matches_fp32_simt(det_state, R, S):
     scale = ref.abs().amax(dim=(0, 1)).clamp_min(1.0)
     err = ((out - ref).abs().amax(dim=(0, 1)) / scale).max().item()
     assert err <= 4e-3, f"tc vs fp32 raw outputs: {err:.3e} of scale"
+
+
+def test_no_grad_forward_runs_the_inference_kernel(det_state):
+    """Under torch.no_grad() (rendering) the parameters still `require_grad`: the forward must nevertheless run the
+    inference kernel -- no 4.7 KB/sample activation stash allocated or written -- and return the training-mode values
+    bit for bit (ops._MLP.forward: the CALLER's grad mode decides, ctx.needs_input_grad does not know about no_grad)."""
+    nets, _ = det_state
+    desc = _lib.MlpDesc(8, 256, 10, 4, 4, 0)
+    R, S = 2048, 64
+    rb, z = mlp_case("coarse", R, S, 3)
+    rb, z = rb.to(DEV), z.to(DEV)
+    flat = flat_of(nets, "coarse")
+    views, off = [], 0
+    for _, shp in O.mlp_param_shapes(desc.D, desc.W, 63, 27, desc.skip):
+        n = int(np.prod(shp))
+        views.append(flat[off:off + n].view(shp).requires_grad_(True))
+        off += n
+    stash_bytes = _lib.lib().lush_mlp_stash_bytes(ctypes.byref(desc), R, S, 1)
+    assert stash_bytes > 500 * 2 ** 20
+    out_train = ops.mlp_apply(rb, z, desc, 1, flat, views)          # grad mode on: stash kept for backward
+    assert out_train.requires_grad
+    ref = out_train.detach().clone()
+    del out_train
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        out = ops.mlp_apply(rb, z, desc, 1, flat, views)
+    torch.cuda.synchronize()
+    assert not out.requires_grad
+    assert torch.cuda.max_memory_allocated() - base < stash_bytes // 4, "a stash was allocated under no_grad"
+    assert torch.equal(out, ref)
 
 
 def test_tc_forward_other_topologies(det_state):

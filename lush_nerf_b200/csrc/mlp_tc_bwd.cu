@@ -141,7 +141,15 @@ __device__ __forceinline__ float grad_scale_from(const unsigned* buf) {
   return exp2f(e);
 }
 
-__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+// one 128-bit read-only load.  (A `*reinterpret_cast<const uint4*>(p)` bound to a const reference parameter is read
+// member by member: four 32-bit loads per lane, each touching 4x the sectors it needs -- head_grads, enc_bwd and
+// ray_grad_reduce did that until round 2, ncu "L2 Theoretical Sectors Global Excessive" 75 %.)
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+  uint4 q;
+  asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p));
+  return q;
+}
+__device__ __forceinline__ void unpack8(const uint4 q, float (&v)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -313,12 +321,12 @@ enc_bwd_kernel(const uint8_t* __restrict__ genc, const float* __restrict__ ray_b
 #pragma unroll
   for (int gq = 0; gq < 8; ++gq) {
     float v0[8], v1[8];
-    if (has_skip) unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 0) * (int64_t)ENC_BYTES + stash_off(8, row, gq)), v0);
+    if (has_skip) unpack8(ldg128(genc + (tile * 2 + 0) * (int64_t)ENC_BYTES + stash_off(8, row, gq)), v0);
     else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v0[i] = 0.f;
     }
-    unpack8(*reinterpret_cast<const uint4*>(genc + (tile * 2 + 1) * (int64_t)ENC_BYTES + stash_off(8, row, gq)), v1);
+    unpack8(ldg128(genc + (tile * 2 + 1) * (int64_t)ENC_BYTES + stash_off(8, row, gq)), v1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) ge[gq * 8 + i] = v0[i] + v1[i];
   }
@@ -626,14 +634,14 @@ head_grads_kernel(const uint8_t* __restrict__ fstash, const float* __restrict__ 
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         float v[8];
-        unpack8(*reinterpret_cast<const uint4*>(rec + h_last_off + stash_off(32, row, w + 8 * a)), v);
+        unpack8(ldg128(rec + h_last_off + stash_off(32, row, w + 8 * a)), v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) aa[a][i] = fmaf(g.w, v[i], aa[a][i]);
       }
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
         float v[8];
-        unpack8(*reinterpret_cast<const uint4*>(rec + hv_off + stash_off(16, row, w + 8 * a)), v);
+        unpack8(ldg128(rec + hv_off + stash_off(16, row, w + 8 * a)), v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           ar[a][0][i] = fmaf(g.x, v[i], ar[a][0][i]);
@@ -703,7 +711,7 @@ ray_grad_reduce_kernel(const float* __restrict__ g_x, const float* __restrict__ 
       const int64_t tile = m / TROWS;
       const int row = (int)(m - tile * TROWS);
       float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(gstash + tile * (int64_t)grec_bytes + grec_v + stash_off(16, row, gq)), v);
+      unpack8(ldg128(gstash + tile * (int64_t)grec_bytes + grec_v + stash_off(16, row, gq)), v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] += v[i];
     }

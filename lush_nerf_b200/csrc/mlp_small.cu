@@ -49,24 +49,48 @@ __device__ __forceinline__ void small_dense(int t, int N, const float* __restric
       if (x == nullptr) continue;
       // every thread streams its own weight row: 16-byte loads when the row segment is aligned (4x fewer L1 requests)
       const bool vec = ((fan | wc) & 3) == 0 && (K & 3) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0;
-#pragma unroll 8                             // 8 weight loads in flight: the row walk is bound by L2 latency, not by FMAs
-      for (int kq = 0; kq < K; kq += 4) {     // shared rows are zero-padded to a multiple of 4
-        float w[4];
-        if (vec) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + wc + kq));
-          w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
-        } else {
+      // The walk is bound by L2 latency, so NB quads of weights are requested one batch ahead of the FMAs that use them
+      // (two explicit register buffers: left to itself the compiler funnelled every load of the unrolled loop through
+      // ONE register quad, i.e. one L2 round trip per four weights -- 65 us for a 4x128 MLP on 1024 rows).
+      constexpr int NB = TM >= 32 ? 4 : 8;
+      const int nq = (K + 3) >> 2;          // shared rows are zero-padded to a multiple of 4
+      auto load_batch = [&](int q0, float (&w)[NB][4]) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) w[j] = (kq + j < K) ? __ldg(wrow + wc + kq + j) : 0.f;
-        }
+        for (int j = 0; j < NB; ++j) {
+          const int kq = (q0 + j) * 4;
+          if (vec && kq < K) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + wc + kq));
+            w[j][0] = w4.x; w[j][1] = w4.y; w[j][2] = w4.z; w[j][3] = w4.w;
+          } else {
 #pragma unroll
-        for (int r = 0; r < TM; ++r) {
-          const float4 a = *reinterpret_cast<const float4*>(x + r * ld + kq);
-          acc[r] = fmaf(a.x, w[0], acc[r]);
-          acc[r] = fmaf(a.y, w[1], acc[r]);
-          acc[r] = fmaf(a.z, w[2], acc[r]);
-          acc[r] = fmaf(a.w, w[3], acc[r]);
+            for (int i = 0; i < 4; ++i) w[j][i] = (!vec && kq + i < K) ? __ldg(wrow + wc + kq + i) : 0.f;
+          }
         }
+      };
+      auto fma_batch = [&](int q0, const float (&w)[NB][4]) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int kq = (q0 + j) * 4;
+          if (kq < K) {
+#pragma unroll
+            for (int r = 0; r < TM; ++r) {
+              const float4 a = *reinterpret_cast<const float4*>(x + r * ld + kq);
+              acc[r] = fmaf(a.x, w[j][0], acc[r]);
+              acc[r] = fmaf(a.y, w[j][1], acc[r]);
+              acc[r] = fmaf(a.z, w[j][2], acc[r]);
+              acc[r] = fmaf(a.w, w[j][3], acc[r]);
+            }
+          }
+        }
+      };
+      float wa[NB][4], wb[NB][4];
+      load_batch(0, wa);
+#pragma unroll 1
+      for (int q0 = 0; q0 < nq; q0 += 2 * NB) {
+        load_batch(q0 + NB, wb);
+        fma_batch(q0, wa);
+        load_batch(q0 + 2 * NB, wa);
+        fma_batch(q0 + NB, wb);
       }
     }
   }
@@ -195,15 +219,33 @@ __device__ __forceinline__ void small_dgrad(int t, int N, int K, const float (*d
     float acc[TM];
 #pragma unroll
     for (int r = 0; r < TM; ++r) acc[r] = 0.f;
-#pragma unroll 8
-    for (int n = 0; n < N; ++n) {
-      const float w = __ldg(Wt + (int64_t)n * fan + wc + t);
+    // weights of 8 output units per batch, requested one batch ahead of their FMAs (explicit double buffer, see small_dense)
+    const float* wcol = Wt + wc + t;
+    auto load8 = [&](int n0, float (&w)[8]) {
 #pragma unroll
-      for (int r4 = 0; r4 < TM; r4 += 4) {
-        const float4 d = *reinterpret_cast<const float4*>(&dzt[n][r4]);
-        acc[r4] = fmaf(d.x, w, acc[r4]); acc[r4 + 1] = fmaf(d.y, w, acc[r4 + 1]);
-        acc[r4 + 2] = fmaf(d.z, w, acc[r4 + 2]); acc[r4 + 3] = fmaf(d.w, w, acc[r4 + 3]);
+      for (int j = 0; j < 8; ++j) w[j] = (n0 + j < N) ? __ldg(wcol + (int64_t)(n0 + j) * fan) : 0.f;
+    };
+    auto fma8 = [&](int n0, const float (&w)[8]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (n0 + j < N) {
+#pragma unroll
+          for (int r4 = 0; r4 < TM; r4 += 4) {
+            const float4 d = *reinterpret_cast<const float4*>(&dzt[n0 + j][r4]);
+            acc[r4] = fmaf(d.x, w[j], acc[r4]); acc[r4 + 1] = fmaf(d.y, w[j], acc[r4 + 1]);
+            acc[r4 + 2] = fmaf(d.z, w[j], acc[r4 + 2]); acc[r4 + 3] = fmaf(d.w, w[j], acc[r4 + 3]);
+          }
+        }
       }
+    };
+    float wa[8], wb[8];
+    load8(0, wa);
+#pragma unroll 1
+    for (int n0 = 0; n0 < N; n0 += 16) {
+      load8(n0 + 8, wb);
+      fma8(n0, wa);
+      load8(n0 + 16, wa);
+      fma8(n0 + 8, wb);
     }
     if (extra) {
       const float w = wextra[t];

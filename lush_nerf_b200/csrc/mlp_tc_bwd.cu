@@ -603,7 +603,7 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
 // ------------------------------------------------------------------------------------------------
 // lane = sample row (coalesced 16-byte loads along a blob column group), warp w owns column groups
 // w, w+8, ... ; per-thread partial sums over all tiles of the block, one shuffle reduction at the end.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_grads_kernel(const uint8_t* __restrict__ fstash, const float* __restrict__ g_out, float* __restrict__ g_params,
                   int64_t M, int64_t ntiles, int frec_bytes, int h_last_off, int hv_off, int64_t alpha_w,
                   int64_t alpha_b, int64_t rgb_w, int64_t rgb_b, int tiles_per_block) {
@@ -623,31 +623,56 @@ head_grads_kernel(const uint8_t* __restrict__ fstash, const float* __restrict__ 
       for (int i = 0; i < 8; ++i) ar[a][c][i] = 0.f;
   const int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
   const int64_t t1 = (t0 + tiles_per_block < ntiles) ? t0 + tiles_per_block : ntiles;
-  for (int64_t tile = t0; tile < t1; ++tile) {
-    const uint8_t* rec = fstash + tile * (int64_t)frec_bytes;
+  // One iteration = 32 rows of a tile: 6 x 16 bytes of stash + the row's g_out per lane.  Every word's register is
+  // refilled for iteration i+1 as soon as iteration i has converted it, so the loads of the next iteration are in flight
+  // while this one is summed: the kernel was bound by one DRAM round trip per iteration (ncu: 68 % long-scoreboard
+  // stalls on the first conversion of each loaded word).
+  const int64_t nit = (t1 - t0) * 4;
+  auto addr_h = [&](int64_t it, int a) {
+    const int row = (int)(it & 3) * 32 + lane;
+    return fstash + (t0 + (it >> 2)) * (int64_t)frec_bytes + h_last_off + stash_off(32, row, w + 8 * a);
+  };
+  auto addr_v = [&](int64_t it, int a) {
+    const int row = (int)(it & 3) * 32 + lane;
+    return fstash + (t0 + (it >> 2)) * (int64_t)frec_bytes + hv_off + stash_off(16, row, w + 8 * a);
+  };
+  auto load_g = [&](int64_t it) {
+    const int64_t m = (t0 + (it >> 2)) * TROWS + (int)(it & 3) * 32 + lane;
+    return (m < M) ? __ldg(reinterpret_cast<const float4*>(g_out) + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  uint4 q[6];
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nit > 0) {
+    g = load_g(0);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) q[a] = ldg128(addr_h(0, a));
+#pragma unroll
+    for (int a = 0; a < 2; ++a) q[4 + a] = ldg128(addr_v(0, a));
+  }
 #pragma unroll 1
-    for (int rb = 0; rb < 4; ++rb) {
-      const int row = rb * 32 + lane;
-      const int64_t m = tile * TROWS + row;
-      const float4 g = (m < M) ? reinterpret_cast<const float4*>(g_out)[m] : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (w == 0) { ab[0] += g.x; ab[1] += g.y; ab[2] += g.z; ab[3] += g.w; }
+  for (int64_t it = 0; it < nit; ++it) {
+    const bool more = it + 1 < nit;       // uniform over the block
+    const float4 gc = g;
+    if (more) g = load_g(it + 1);
+    if (w == 0) { ab[0] += gc.x; ab[1] += gc.y; ab[2] += gc.z; ab[3] += gc.w; }
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        float v[8];
-        unpack8(ldg128(rec + h_last_off + stash_off(32, row, w + 8 * a)), v);
+    for (int a = 0; a < 4; ++a) {
+      float v[8];
+      unpack8(q[a], v);
+      if (more) q[a] = ldg128(addr_h(it + 1, a));     // this word's register is free: refill it for the next iteration
 #pragma unroll
-        for (int i = 0; i < 8; ++i) aa[a][i] = fmaf(g.w, v[i], aa[a][i]);
-      }
+      for (int i = 0; i < 8; ++i) aa[a][i] = fmaf(gc.w, v[i], aa[a][i]);
+    }
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        float v[8];
-        unpack8(ldg128(rec + hv_off + stash_off(16, row, w + 8 * a)), v);
+    for (int a = 0; a < 2; ++a) {
+      float v[8];
+      unpack8(q[4 + a], v);
+      if (more) q[4 + a] = ldg128(addr_v(it + 1, a));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          ar[a][0][i] = fmaf(g.x, v[i], ar[a][0][i]);
-          ar[a][1][i] = fmaf(g.y, v[i], ar[a][1][i]);
-          ar[a][2][i] = fmaf(g.z, v[i], ar[a][2][i]);
-        }
+      for (int i = 0; i < 8; ++i) {
+        ar[a][0][i] = fmaf(gc.x, v[i], ar[a][0][i]);
+        ar[a][1][i] = fmaf(gc.y, v[i], ar[a][1][i]);
+        ar[a][2][i] = fmaf(gc.z, v[i], ar[a][2][i]);
       }
     }
   }

@@ -609,7 +609,7 @@ def main():
                 "mlp_fwd (pack + mlp_tc_fwd_kernel, stash written)": {
                     "ms_per_step": fwd_ms / args.steps, "tflops": f / (fwd_ms * 1e-3) / 1e12,
                     "frac_of_tensor_peak": f / (fwd_ms * 1e-3) / 1e12 / peaks["tflops"]},
-                "mlp_bwd (dgrad chain + wgrad GEMM + head/ray reductions)": {
+                "mlp_bwd (dgrad chain incl. head gradients + wgrad GEMM + ray reductions)": {
                     "ms_per_step": bwd_ms / args.steps, "tflops": 2 * f / (bwd_ms * 1e-3) / 1e12,
                     "frac_of_tensor_peak": 2 * f / (bwd_ms * 1e-3) / 1e12 / peaks["tflops"]},
                 "noise MLP (fp32 SIMT, 4x128, 1024 rows)": {"ms_per_step": simt_ms / args.steps},

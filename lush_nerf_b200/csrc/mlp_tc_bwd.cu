@@ -161,7 +161,15 @@ __device__ __forceinline__ void unpack8(const uint4 q, float (&v)[8]) {
 // shared-memory map of the dgrad kernel behind the ring and the activation tile
 struct DgSmem {
   static constexpr int G16 = DgradRing::FREE0;                 // 2 x [128 x 16]: (g_r, g_g, g_b, g_sigma, 0...) * scale
-  static constexpr int TOTAL = G16 + 2 * CH_X16_BYTES;
+  static constexpr int RED = G16 + 2 * CH_X16_BYTES;           // head-gradient partial sums of the prologue warps (fp32)
+  static constexpr int RED_FLOATS = 4 * 256 + 8 * 384 + 128 * 4;
+  static constexpr int TOTAL = RED + RED_FLOATS * 4;
+};
+// the head gradients (sigma head 256 -> 1, rgb head 128 -> 3) summed by the dgrad kernel's prologue warps
+struct HeadFold {
+  float* g_params;
+  int h_last_off, hv_off;
+  int64_t alpha_w, alpha_b, rgb_w, rgb_b;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
 mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ g_out,
                     const unsigned* __restrict__ scale_buf, const uint8_t* __restrict__ fstash,
                     uint8_t* __restrict__ gstash, uint8_t* __restrict__ genc, int64_t M, ChainPlan C, FwdPlan P,
-                    BwdPlan Bp) {
+                    BwdPlan Bp, HeadFold HF) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ ChainBars B;
   __shared__ uint32_t tmem_base_s;
@@ -211,6 +219,14 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
     // =========================== prologue warpgroup: loss-scaled head gradients of the NEXT tile ===========
     const int row = tid - CH_WG_PRO * 32;
     const float scale = grad_scale_from(scale_buf);
+    // head gradients: these warps are idle once the tile's 2 KB operand is built, so they also sum
+    //   dW_alpha[c] = sum_m g_sigma[m] H_{D-1}[m][c]      dW_rgb[k][c] = sum_m g_k[m] HV[m][c]      (+ the head biases)
+    // over the tiles of this CTA -- fp32 g_out x the forward stash, as the separate head_grads kernel did.
+    // Thread (lane = column group, warp = row quarter) for H_{D-1}; (tid & 15 = column group, tid >> 4 = 16-row block) for HV.
+    float aa[8], ar[3][8], ab[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { aa[i] = 0.f; ar[0][i] = 0.f; ar[1][i] = 0.f; ar[2][i] = 0.f; }
+    const int cgV = row & 15, oV = row >> 4;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int b = (int)(it & 1);
@@ -222,6 +238,81 @@ mlp_tc_dgrad_kernel(const uint8_t* __restrict__ bstream, const float* __restrict
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.pro_ready[b]);
+      {
+        ab[0] += g.x; ab[1] += g.y; ab[2] += g.z; ab[3] += g.w;
+        const uint8_t* rec = fstash + tile * (int64_t)P.rec_bytes;
+        const int64_t m0 = tile * TROWS;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) {          // sigma head: rows [32 warp + r0, +8) of column group `lane`
+          uint4 qv[8];
+          float gs[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = 32 * (warp - CH_WG_PRO) + r0 + j;
+            qv[j] = ldg128(rec + HF.h_last_off + stash_off(32, r, lane));
+            gs[j] = (m0 + r < M) ? __ldg(g_out + (m0 + r) * 4 + 3) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v[8];
+            unpack8(qv[j], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) aa[i] = fmaf(gs[j], v[i], aa[i]);
+          }
+        }
+#pragma unroll 1
+        for (int r0 = 0; r0 < 16; r0 += 8) {          // rgb head: rows [16 oV + r0, +8) of column group cgV
+          uint4 qv[8];
+          float4 gr[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = 16 * oV + r0 + j;
+            qv[j] = ldg128(rec + HF.hv_off + stash_off(16, r, cgV));
+            gr[j] = (m0 + r < M) ? __ldg(reinterpret_cast<const float4*>(g_out) + m0 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v[8];
+            unpack8(qv[j], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              ar[0][i] = fmaf(gr[j].x, v[i], ar[0][i]);
+              ar[1][i] = fmaf(gr[j].y, v[i], ar[1][i]);
+              ar[2][i] = fmaf(gr[j].z, v[i], ar[2][i]);
+            }
+          }
+        }
+      }
+    }
+    {                          // partial sums of the 4 row quarters / 8 row blocks / 128 rows -> one atomic per gradient and CTA
+      float* red = reinterpret_cast<float*>(smem + DgSmem::RED);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        red[(warp - CH_WG_PRO) * 256 + lane * 8 + i] = aa[i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) red[1024 + oV * 384 + c * 128 + cgV * 8 + i] = ar[c][i];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red[4096 + row * 4 + c] = ab[c];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int col = 2 * row + k;
+        atomicAdd(HF.g_params + HF.alpha_w + col, red[col] + red[256 + col] + red[512 + col] + red[768 + col]);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int e = row + 128 * k;
+        float t = 0.f;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) t += red[1024 + o * 384 + e];
+        atomicAdd(HF.g_params + HF.rgb_w + e, t);
+      }
+      if (row < 4) {
+        float t = 0.f;
+        for (int u = 0; u < 128; ++u) t += red[4096 + u * 4 + row];
+        atomicAdd(HF.g_params + (row < 3 ? HF.rgb_b + row : HF.alpha_b), t);
+      }
     }
   } else if (warp < CH_WARP_PRODUCER) {
     // =========================== epilogue warpgroups ===========================
@@ -599,109 +690,6 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 3a: head gradients (sigma head 256->1 and rgb head 128->3), fp32 g_out x fp16 stash
-// ------------------------------------------------------------------------------------------------
-// lane = sample row (coalesced 16-byte loads along a blob column group), warp w owns column groups
-// w, w+8, ... ; per-thread partial sums over all tiles of the block, one shuffle reduction at the end.
-__global__ void __launch_bounds__(256, 2)
-head_grads_kernel(const uint8_t* __restrict__ fstash, const float* __restrict__ g_out, float* __restrict__ g_params,
-                  int64_t M, int64_t ntiles, int frec_bytes, int h_last_off, int hv_off, int64_t alpha_w,
-                  int64_t alpha_b, int64_t rgb_w, int64_t rgb_b, int tiles_per_block) {
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  float aa[4][8];      // sigma head: 4 column groups x 8 columns
-  float ar[2][3][8];   // rgb head: 2 column groups x 3 channels x 8 columns
-  float ab[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) aa[a][i] = 0.f;
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ar[a][c][i] = 0.f;
-  const int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
-  const int64_t t1 = (t0 + tiles_per_block < ntiles) ? t0 + tiles_per_block : ntiles;
-  // One iteration = 32 rows of a tile: 6 x 16 bytes of stash + the row's g_out per lane.  Every word's register is
-  // refilled for iteration i+1 as soon as iteration i has converted it, so the loads of the next iteration are in flight
-  // while this one is summed: the kernel was bound by one DRAM round trip per iteration (ncu: 68 % long-scoreboard
-  // stalls on the first conversion of each loaded word).
-  const int64_t nit = (t1 - t0) * 4;
-  auto addr_h = [&](int64_t it, int a) {
-    const int row = (int)(it & 3) * 32 + lane;
-    return fstash + (t0 + (it >> 2)) * (int64_t)frec_bytes + h_last_off + stash_off(32, row, w + 8 * a);
-  };
-  auto addr_v = [&](int64_t it, int a) {
-    const int row = (int)(it & 3) * 32 + lane;
-    return fstash + (t0 + (it >> 2)) * (int64_t)frec_bytes + hv_off + stash_off(16, row, w + 8 * a);
-  };
-  auto load_g = [&](int64_t it) {
-    const int64_t m = (t0 + (it >> 2)) * TROWS + (int)(it & 3) * 32 + lane;
-    return (m < M) ? __ldg(reinterpret_cast<const float4*>(g_out) + m) : make_float4(0.f, 0.f, 0.f, 0.f);
-  };
-  uint4 q[6];
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (nit > 0) {
-    g = load_g(0);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) q[a] = ldg128(addr_h(0, a));
-#pragma unroll
-    for (int a = 0; a < 2; ++a) q[4 + a] = ldg128(addr_v(0, a));
-  }
-#pragma unroll 1
-  for (int64_t it = 0; it < nit; ++it) {
-    const bool more = it + 1 < nit;       // uniform over the block
-    const float4 gc = g;
-    if (more) g = load_g(it + 1);
-    if (w == 0) { ab[0] += gc.x; ab[1] += gc.y; ab[2] += gc.z; ab[3] += gc.w; }
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      float v[8];
-      unpack8(q[a], v);
-      if (more) q[a] = ldg128(addr_h(it + 1, a));     // this word's register is free: refill it for the next iteration
-#pragma unroll
-      for (int i = 0; i < 8; ++i) aa[a][i] = fmaf(gc.w, v[i], aa[a][i]);
-    }
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      float v[8];
-      unpack8(q[4 + a], v);
-      if (more) q[4 + a] = ldg128(addr_v(it + 1, a));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        ar[a][0][i] = fmaf(gc.x, v[i], ar[a][0][i]);
-        ar[a][1][i] = fmaf(gc.y, v[i], ar[a][1][i]);
-        ar[a][2][i] = fmaf(gc.z, v[i], ar[a][2][i]);
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float t = warp_sum(aa[a][i]);
-      if (lane == 0) atomicAdd(g_params + alpha_w + (w + 8 * a) * 8 + i, t);
-    }
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float t = warp_sum(ar[a][c][i]);
-        if (lane == 0) atomicAdd(g_params + rgb_w + c * 128 + (w + 8 * a) * 8 + i, t);
-      }
-  if (w == 0) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float t = warp_sum(ab[c]);
-      if (lane == 0) atomicAdd(g_params + (c < 3 ? rgb_b + c : alpha_b), t);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // stage 3b: per-ray reduction  d/d(o), d/d(d) from per-sample d/dx;  d/d(viewdirs) from sum_s dZv
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -891,8 +879,9 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
                     "mlp_bwd(tc): dgrad smem attr");
     if (rc) return rc;
     int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    const HeadFold HF = {g_params, P.rec_h0 + (L.D - 1) * H_BYTES, P.rec_hv, L.alpha_w, L.alpha_b, L.rgb_w, L.rgb_b};
     mlp_tc_dgrad_kernel<<<grid, CH_THREADS, smem, st>>>((const uint8_t*)bstream, g_out, scale_buf, fstash, gstash, genc,
-                                                       M, C, P, B);
+                                                       M, C, P, B, HF);
     LUSH_LAUNCH_CHECK("mlp_tc_dgrad");
   }
   {
@@ -909,14 +898,6 @@ int lush_mlp_tc_bwd(const MlpLayout& L, const lush_mlp_desc* desc, const float* 
     fv_post_kernel<<<(TW * TW + 128 * TW + TW + 255) / 256, 256, 0, st>>>(aux, params, g_params, L.views_w, L.W + L.in_ch_v,
                                                                          L.views_b, L.feat_w, L.feat_b);
     LUSH_LAUNCH_CHECK("fv_post");
-  }
-  {
-    const int tpb = (int)((ntiles + 2 * kNumSMs - 1) / (2 * kNumSMs));
-    const int nblk = (int)((ntiles + tpb - 1) / tpb);
-    head_grads_kernel<<<nblk, 256, 0, st>>>(fstash, g_out, g_params, M, ntiles, P.rec_bytes,
-                                            P.rec_h0 + (L.D - 1) * H_BYTES, P.rec_hv, L.alpha_w, L.alpha_b, L.rgb_w,
-                                            L.rgb_b, tpb);
-    LUSH_LAUNCH_CHECK("head_grads");
   }
   if (need_in) {
     enc_bwd_kernel<<<(unsigned)ntiles, 128, 0, st>>>(genc, ray_batch, ray_stride, z, scale_buf, gx, M, S, desc->L_pts,

@@ -716,23 +716,48 @@ ray_grad_reduce_kernel(const float* __restrict__ g_x, const float* __restrict__ 
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) { go[c] = warp_sum(go[c]); gd[c] = warp_sum(gd[c]); }
-  // sum of the views-layer dZ over the samples of this ray
-  for (int gq = 0; gq < 16; ++gq) {
-    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int s = lane; s < S; s += 32) {
-      const int64_t m = r * S + s;
-      const int64_t tile = m / TROWS;
-      const int row = (int)(m - tile * TROWS);
-      float v[8];
-      unpack8(ldg128(gstash + tile * (int64_t)grec_bytes + grec_v + stash_off(16, row, gq)), v);
+  // sum of the views-layer dZ over the samples of this ray: four column groups per pass, all of their loads in flight
+  // together (one DRAM round trip per pass instead of one per column group)
+#pragma unroll 1
+  for (int g0 = 0; g0 < 16; g0 += 4) {
+    float a[4][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] += v[i];
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[q][i] = 0.f;
+#pragma unroll 1
+    for (int s0 = lane; s0 < S; s0 += 64) {
+      uint4 qv[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int s = s0 + 32 * u;
+        const int64_t m = r * S + (s < S ? s : s0);
+        const int64_t tile = m / TROWS;
+        const int row = (int)(m - tile * TROWS);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          qv[u][q] = ldg128(gstash + tile * (int64_t)grec_bytes + grec_v + stash_off(16, row, g0 + q));
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (s0 + 32 * u < S) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+            unpack8(qv[u][q], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[q][i] += v[i];
+          }
+        }
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float t = warp_sum(a[i]);
-      if (lane == i) s_sum[w][gq * 8 + i] = t;
-    }
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = warp_sum(a[q][i]);
+        if (lane == i) s_sum[w][(g0 + q) * 8 + i] = t;
+      }
   }
   __syncwarp();
   float ge = 0.f;   // lane q < in_ch_v: d/d gamma(v)[q]

@@ -525,6 +525,31 @@ static void make_wgrad_plan(const MlpLayout& L, const FwdPlan& P, const BwdPlan&
   }
 }
 
+// 32 consecutive fp32 gradients of one output row, dst = address of value 0, LEAD = values before the first 16-byte
+// boundary; only the first `nreal` values exist (the rest is K padding of the GEMM)
+template <int LEAD>
+__device__ __forceinline__ void wgrad_flush32(float* dst, const uint32_t (&r)[32], float inv_scale, int nreal) {
+#pragma unroll
+  for (int j = 0; j < LEAD; ++j)
+    if (j < nreal) atomicAdd(dst + j, __uint_as_float(r[j]) * inv_scale);
+#pragma unroll
+  for (int j = LEAD; j + 4 <= 32; j += 4) {
+    if (j + 4 <= nreal) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j]) * inv_scale),
+                   "f"(__uint_as_float(r[j + 1]) * inv_scale), "f"(__uint_as_float(r[j + 2]) * inv_scale),
+                   "f"(__uint_as_float(r[j + 3]) * inv_scale)
+                   : "memory");
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (j + i < nreal) atomicAdd(dst + j + i, __uint_as_float(r[j + i]) * inv_scale);
+    }
+  }
+#pragma unroll
+  for (int j = LEAD + 4 * ((32 - LEAD) / 4); j < 32; ++j)
+    if (j < nreal) atomicAdd(dst + j, __uint_as_float(r[j]) * inv_scale);
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1)
 mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restrict__ gstash,
                     const unsigned* __restrict__ scale_buf, float* __restrict__ g_params, float* __restrict__ aux,
@@ -668,27 +693,26 @@ mlp_tc_wgrad_kernel(const uint8_t* __restrict__ fstash, const uint8_t* __restric
       tc_fence_after();
       for (int h = 0; h < J.nout / 128; ++h) {
         float* dst = (J.to_aux ? aux : g_params + J.w_off) + (int64_t)(h * 128 + row) * J.fan_in + J.col0;
-        // a lane owns one output row: its 32 values of a column block are contiguous in dW.  Where the row is 16-byte
-        // aligned they leave as 8 four-float reductions instead of 32 scalar ones (a quarter of the L2 atomic
-        // operations: ncu counted 32 sectors per scalar REDG, 20 M sector-atomics per launch)
-        const bool vec = !J.to_aux && (J.fan_in & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+        // a lane owns one output row: its 32 values of a column block are contiguous in dW and leave as four-float
+        // reductions on 16-byte boundaries instead of 32 scalar ones (a quarter of the L2 atomic operations: ncu counted
+        // 32 sectors per scalar REDG, 20 M sector-atomics per launch)
+        // (rows of a 319- or 283-column weight start at every alignment: the lane's first 0..3 values go as scalars)
+        const int lead = (4 - (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3;
 #pragma unroll 1
         for (int cc = 0; cc < J.kin; cc += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_base + tlane + h * 256 + cc, r);
           tmem_ld_wait();
-          if (vec && cc + 32 <= J.kin_real) {
+          if (J.to_aux) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + cc + j),
-                           "f"(__uint_as_float(r[j]) * inv_scale), "f"(__uint_as_float(r[j + 1]) * inv_scale),
-                           "f"(__uint_as_float(r[j + 2]) * inv_scale), "f"(__uint_as_float(r[j + 3]) * inv_scale)
-                           : "memory");
+            for (int j = 0; j < 32; ++j) atomicAdd(aux + (cc + j) * 128 + row, __uint_as_float(r[j]) * inv_scale);   // T^T[k][n]: coalesced
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (J.to_aux) atomicAdd(aux + (cc + j) * 128 + row, __uint_as_float(r[j]) * inv_scale);   // T^T[k][n]: coalesced
-              else if (cc + j < J.kin_real) atomicAdd(dst + cc + j, __uint_as_float(r[j]) * inv_scale);
+            const int nreal = J.kin_real - cc;      // values of this block that exist (>= 32: all)
+            switch (lead) {
+              case 0: wgrad_flush32<0>(dst + cc, r, inv_scale, nreal); break;
+              case 1: wgrad_flush32<1>(dst + cc, r, inv_scale, nreal); break;
+              case 2: wgrad_flush32<2>(dst + cc, r, inv_scale, nreal); break;
+              default: wgrad_flush32<3>(dst + cc, r, inv_scale, nreal); break;
             }
           }
         }

@@ -15,11 +15,20 @@
 namespace lush {
 
 constexpr int SM_THREADS = 128;
-constexpr int SM_FWD_TM = 8;
+// rows per CTA below SM_BIG_ROWS rows (training: N_rand = 1024 rows).  Measured on B200 (tools/jobs/r2_run40.sh, r2_run41.sh;
+// forward + backward per step): 8 / 16 -> 0.160 ms, 4 / 8 -> 0.126, 2 / 4 -> 0.142, 4 / 4 -> 0.116: with one warp per SM
+// sub-partition nothing hides a CTA's latencies, so more, smaller CTAs win until the per-CTA weight walk dominates.
+#ifndef LUSH_SM_FWD_TM
+#define LUSH_SM_FWD_TM 4
+#endif
+#ifndef LUSH_SM_BWD_TM
+#define LUSH_SM_BWD_TM 4
+#endif
+constexpr int SM_FWD_TM = LUSH_SM_FWD_TM;
 constexpr int SM_FWD_TM_BIG = 32;  // rows per CTA from SM_BIG_ROWS rows on (rendering: a 32 768-ray chunk): every CTA walks
 constexpr int64_t SM_BIG_ROWS = 4096;   // all 229 KB of weights once per row tile, so 4x the rows = 1/4 of the L2 traffic;
                                    // same FMA order per output, bit-identical results
-constexpr int SM_BWD_TM = 16;
+constexpr int SM_BWD_TM = LUSH_SM_BWD_TM;
 constexpr int SM_XLD = 192;        // row stride of the layer-input tile (>= W + in_ch, W <= 128, in_ch <= 63)
 
 struct SmallStash {                // same arrays as SimtStash in mlp_simt.cu
